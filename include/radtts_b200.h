@@ -62,6 +62,98 @@ RADTTS_API int radtts_mas_forward(const float* attn, int is_prob, const int64_t*
                        int T1, int T2, float* attn_hard, int32_t* frame_to_token, int32_t* durations, void* ws,
                        size_t ws_bytes, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Packed frame layout ("frame plan").
+ * The reference keeps zero-padded (B, C, T') activations and re-derives masks with a host sync in every
+ * layer (get_mask_from_lengths, reference common.py:86-97, called from common.py:567 etc.).  Here the
+ * valid frames of all utterances are packed channels-last into one row axis with 16 zero rows between
+ * utterances; the plan (row offsets, per-row position metadata) is built on the device from the lengths.
+ *   lens     (B) int64 device; frames per utterance = lens[b] / divisor (clamped to [0, Tmax]).
+ *   plan     device buffer of radtts_frameplan_bytes(B, Tmax) bytes.
+ *   rows     radtts_frameplan_rows(B, Tmax): allocated rows (multiple of 128) of every packed buffer.
+ * ---------------------------------------------------------------------------------------------- */
+RADTTS_API size_t radtts_frameplan_bytes(int B, int Tmax);
+RADTTS_API int radtts_frameplan_rows(int B, int Tmax);
+RADTTS_API int radtts_frameplan_build(const int64_t* lens, int divisor, int B, int Tmax, void* plan, void* stream);
+
+/* (B, C, T) float32  <->  packed rows.  Implements the reference's squeeze/unsqueeze
+ * (nn.Unfold((g,1), stride g) reference radtts.py:165-169,414 and fold radtts.py:308-318) as pure indexing:
+ * packed[row0[b] + t'][col_off + c*g + k] = x[b][c][g*t' + k].
+ *   pack:   dst is float32 (dst_bf16 = 0) or bfloat16 (dst_bf16 = 1), row stride ld elements; columns
+ *           [col_off, col_off + ncols_pad) are written (zeros beyond C*g and on gap rows).
+ *   unpack: src float32 packed, dst (B, C, Tmax*g) float32, zeros beyond each utterance's length. */
+RADTTS_API int radtts_pack_frames(const float* src, int B, int C, int T, int g, const void* plan, int Tmax, void* dst,
+                                  int dst_bf16, int ld, int col_off, int ncols_pad, void* stream);
+RADTTS_API int radtts_unpack_frames(const float* src, int ld, int col_off, const void* plan, int B, int Tmax, int C,
+                                    int g, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Kernel 2 -- decoder flow step: Invertible1x1ConvLUS + AffineTransformationLayer(WN) + log-det pieces.
+ * Replaces: FlowStep.forward (reference radtts.py:51-59), Invertible1x1ConvLUS.forward (common.py:407-428,
+ * the 1x1 conv itself; W = P L U and log|det| stay a few tiny host-side torch ops), WN.forward
+ * (common.py:560-578) with ConvNorm/PartialConv1d (common.py:145-154, partialconv1d.py:35-71) and
+ * AffineTransformationLayer.forward with scaling_fn 'tanh' (common.py:782-784,810-832).
+ *
+ * precision: RADTTS_PREC_FP32 -- fp32 activations/weights, fp32 FMA (parity path, rtol 1e-3 bar);
+ *            RADTTS_PREC_BF16 -- bf16 activations/weights on tcgen05 tensor cores, fp32 accumulate; z, the
+ *                                1x1 conv, the coupling and log_s stay fp32 as in the reference under autocast.
+ * ---------------------------------------------------------------------------------------------- */
+#define RADTTS_PREC_FP32 0
+#define RADTTS_PREC_BF16 1
+#define RADTTS_MAX_LAYERS 8
+
+typedef struct radtts_flow_dims {
+  int z_ld;      /* row width of the packed z buffers (n_mel_channels * n_group_size = 160) */
+  int c_off;     /* first active column of this flow (2 * number of early exits so far) */
+  int c_active;  /* channels this flow transforms (z_ld - c_off) */
+  int n_ctx;     /* conditioning channels (1040) */
+  int n_ch;      /* WN channels (1024) */
+  int n_layers;  /* WN layers (4) */
+  int ksize;     /* WN kernel size (5) */
+  int partial_padding; /* 1: PartialConv1d renormalisation (decoder_use_partial_padding, default) */
+  int scaling;   /* coupling scale fn: 0 tanh, 1 exp, 2 sigmoid, 3 translate (common.py:775-787) */
+} radtts_flow_dims;
+
+/* Effective (weight-norm already applied) float32 weights in the reference's PyTorch layouts. */
+typedef struct radtts_flow_weights {
+  const float* w_inv;   /* (c_active, c_active): W for forward, W^-1 for inverse */
+  const float* w_start; /* (n_ch, h + n_ctx), input channel order [z0 | context] (common.py:562) */
+  const float* b_start; /* (n_ch) */
+  const float* w_in[RADTTS_MAX_LAYERS]; /* (n_ch, n_ch, ksize), dilation 2^i */
+  const float* b_in[RADTTS_MAX_LAYERS];
+  const float* w_rs[RADTTS_MAX_LAYERS]; /* (n_ch, n_ch) */
+  const float* b_rs[RADTTS_MAX_LAYERS];
+  const float* w_end;   /* (2h, n_ch): rows [0,h) raw scale, [h,2h) translation */
+  const float* b_end;   /* (2h) */
+} radtts_flow_weights;
+
+/* Packed activation buffers of one flow step; caller-allocated, `rows` = radtts_frameplan_rows().
+ * "act" element type is float32 (PREC_FP32) or bfloat16 (PREC_BF16). */
+typedef struct radtts_flow_buffers {
+  const void* ctx; /* act [rows][ctx_ld], ctx_ld = round_up(n_ctx, 64): packed conditioning */
+  const float* zin;/* [rows][z_ld] input of the flow */
+  float* zmid;     /* [rows][z_ld] forward: after the 1x1 conv; inverse: after the inverse coupling */
+  float* zout;     /* [rows][z_ld] output of the flow */
+  void* z0;        /* act [rows][128] copy of the untransformed half (zero padded) */
+  void* x;         /* act [n_layers + 1][rows][n_ch]: `start` output then every in_layer output */
+  void* r;         /* act [rows][n_layers * n_ch]: softplus(res_skip) of every layer, K-concatenated */
+  float* params;   /* [rows][z_ld] interleaved (raw scale, translation) pairs (forward; may be NULL) */
+  float* log_s;    /* [rows][z_ld / 2] (forward only) */
+} radtts_flow_buffers;
+
+/* Re-layouts the weights for the GEMM kernels (tap-major K, interleaved `end`, bf16 cast, and -- when
+ * want_backward -- the transposed copies the dgrad GEMMs read).  Run once per optimizer step (training) or
+ * once per model (inference). */
+RADTTS_API size_t radtts_flow_prepared_bytes(const radtts_flow_dims* dims, int precision, int want_backward);
+RADTTS_API int radtts_flow_prepare(const radtts_flow_dims* dims, const radtts_flow_weights* w, int inverse,
+                                   int precision, int want_backward, void* prepared, size_t prepared_bytes,
+                                   void* stream);
+RADTTS_API int radtts_flowstep_forward(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
+                                       int Tmax, const radtts_flow_buffers* buf, int precision, void* stream);
+RADTTS_API int radtts_flowstep_inverse(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
+                                       int Tmax, const radtts_flow_buffers* buf, int precision, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,7 +67,111 @@ def gen_mas(ns):
     print("wrote mas_cases.npz", os.path.getsize(os.path.join(GOLD, "mas_cases.npz")), "bytes")
 
 
-GENERATORS = {"mas": gen_mas}
+def _ref_model(ns, config_name):
+    import json
+    import torch
+    from radtts_b200 import synth
+    cfg = json.load(open(os.path.join(ns.root, "configs", config_name)))
+    torch.manual_seed(0)
+    model = ns.radtts.RADTTS(**cfg["model_config"]).eval()
+    sd = synth.synth_state_dict([(k, v.shape) for k, v in model.state_dict().items()], seed=1234)
+    model.load_state_dict(sd, strict=True)   # strict: names and shapes of the product model == reference
+    return model, cfg, sd
+
+
+def _param_summary(t):
+    f = t.detach().double().flatten()
+    return np.array([f.sum().item(), f.norm().item()], dtype=np.float64), f[::1009][:64].float().numpy()
+
+
+def gen_radtts_forward(ns):
+    """config_ljs_radtts: full RADTTS.forward (eval mode) with binarize_attention=True, the RADTTSLoss terms,
+    then -- on the captured decoder inputs -- the decoder loop's gradients and the sampling direction."""
+    import torch
+    from radtts_b200 import synth
+    model, cfg, sd = _ref_model(ns, "config_ljs_radtts.json")
+    B, T1, T2 = 3, 70, 24
+    batch = synth.synth_batch(B, T1, T2, seed=1234)
+    captured = {}
+    def grab(module, inp, out):
+        captured.setdefault("context", inp[1].detach().clone())  # hooks must return None to leave `out` alone
+
+    h = model.flows[0].register_forward_hook(grab)
+    with torch.no_grad():
+        out = model(batch["mel"], batch["speaker_ids"], batch["text"], batch["in_lens"], batch["out_lens"],
+                    binarize_attention=True, attn_prior=batch["attn_prior"])
+    h.remove()
+    g = {"z_mel": out["z_mel"].numpy(), "attn_soft": out["attn_soft"].numpy(), "attn": out["attn"].numpy(),
+         "attn_logprob": out["attn_logprob"].numpy(), "text_embeddings": out["text_embeddings"].numpy(),
+         "context": captured["context"].numpy(),
+         "log_det_W": np.array([float(x) for x in out["log_det_W_list"]], dtype=np.float32)}
+    for i, ls in enumerate(out["log_s_list"]):
+        g["log_s_%d" % i] = ls.numpy()
+    # losses (loss.py:147-203); compute_flow_loss mutates log_det_W_list[0] in place -> saved above first
+    crit = ns.loss.RADTTSLoss(sigma=1.0, n_group_size=2, loss_weights=cfg["train_config"]["loss_weights"])
+    with torch.no_grad():
+        ld = crit(out, batch["in_lens"], batch["out_lens"])
+        g["loss_mel"] = np.float32(ld["loss_mel"][0])
+        g["loss_prior_mel"] = np.float32(ld["loss_prior_mel"][0])
+        g["loss_ctc"] = np.float32(ld["loss_ctc"][0])
+        g["loss_binarization"] = np.float32(ns.loss.AttentionBinarizationLoss()(out["attn"], out["attn_soft"]))
+
+    # ---- decoder sub-path with gradients (context and mel as leaves; reference radtts.py:414,431-444) ----
+    model.zero_grad()
+    mel = batch["mel"].clone().requires_grad_(True)
+    ctx = captured["context"].clone().requires_grad_(True)
+    z = model.unfold(mel.unsqueeze(-1))
+    lens = batch["out_lens"] // 2
+    z_out, log_s_list, logdets = [], [], []
+    for i, flow in enumerate(model.flows):
+        if i in model.exit_steps:
+            z_out.append(z[:, :2])
+            z = z[:, 2:]
+        z, ld_w, ls = flow(z, ctx, seq_lens=lens)
+        log_s_list.append(ls)
+        logdets.append(ld_w)
+    z_out.append(z)
+    z_mel = torch.cat(z_out, 1)
+    n_el = batch["out_lens"].sum() // 2
+    mask = ns.common.get_mask_from_lengths(lens)[:, None].float()
+    loss, _ = ns.loss.compute_flow_loss(z_mel, [x.clone() for x in logdets], log_s_list, n_el, 160, mask, 1.0)
+    loss.backward()
+    assert np.allclose(z_mel.detach().numpy(), g["z_mel"], atol=1e-6)
+    g["dec_loss"] = np.float32(loss.item())
+    g["g_mel"] = mel.grad.numpy()
+    g["g_context"] = ctx.grad.numpy()
+    names, sums, samples = [], [], []
+    for k, p in model.named_parameters():
+        if k.startswith("flows.") and p.grad is not None:
+            sm, sp = _param_summary(p.grad)
+            names.append(k); sums.append(sm); samples.append(np.pad(sp, (0, 64 - len(sp))))
+    g["grad_names"] = np.array(names)
+    g["grad_sums"] = np.stack(sums)
+    g["grad_samples"] = np.stack(samples)
+
+    # ---- sampling direction (reference radtts.py:652-677) on the same context ----
+    rng = np.random.default_rng(4321)
+    residual = torch.from_numpy(rng.standard_normal((B, 160, T1 // 2), dtype=np.float32) * 0.8)
+    with torch.no_grad():
+        stack = model.exit_steps.copy()
+        x = residual[:, len(stack) * 2:]
+        rest = residual[:, :len(stack) * 2]
+        for i, flow in enumerate(reversed(model.flows)):
+            cur = len(model.flows) - i - 1
+            x = flow(x, ctx.detach(), inverse=True, seq_lens=lens)
+            if stack and cur == stack[-1]:
+                stack.pop()
+                x = torch.cat((rest[:, len(stack) * 2:], x), 1)
+                rest = rest[:, :len(stack) * 2]
+        mel_inf = model.fold(x)
+    g["residual"] = residual.numpy()
+    g["mel_inferred"] = mel_inf.numpy()
+    np.savez_compressed(os.path.join(GOLD, "radtts_forward.npz"), **g)
+    print("wrote radtts_forward.npz", os.path.getsize(os.path.join(GOLD, "radtts_forward.npz")), "bytes;",
+          "loss_mel %.5f ctc %.5f bin %.5f" % (g["loss_mel"], g["loss_ctc"], g["loss_binarization"]))
+
+
+GENERATORS = {"mas": gen_mas, "radtts_forward": gen_radtts_forward}
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)

@@ -1,0 +1,458 @@
+// Kernel 2 (host orchestration + small kernels): frame plan, pack / unpack, weight re-layout, and the
+// decoder flow step (invertible 1x1 conv -> WN parameter net -> affine coupling) in both directions.
+// The contractions run through rowgemm_simt (fp32) or rowgemm_tc (bf16 tcgen05); see rowgemm.cuh.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "flow_layout.cuh"
+#include "frameplan.cuh"
+#include "rowgemm.cuh"
+#include "rowgemm_tc.cuh"
+
+namespace rb {
+
+// ====================================================================================================
+// frame plan
+// ====================================================================================================
+__global__ void __launch_bounds__(1024) frameplan_kernel(const int64_t* __restrict__ lens, int divisor, int B,
+                                                         int Tmax, int rows_alloc, int* __restrict__ plan) {
+  int* hdr = plan;
+  int* row0 = plan + 8;
+  int* len = plan + 8 + B;
+  int* pos = plan + plan_meta_off(B);
+  int* rem = pos + rows_alloc;
+  int* utt = rem + rows_alloc;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int r = kGap;
+    for (int b = 0; b < B; ++b) {
+      long long l = lens[b] / divisor;
+      int li = (int)(l < 0 ? 0 : (l > Tmax ? Tmax : l));
+      row0[b] = r;
+      len[b] = li;
+      r += li + kGap;
+    }
+    hdr[0] = r;  // rows in use (ends with a gap)
+    hdr[1] = B; hdr[2] = Tmax; hdr[3] = rows_alloc; hdr[4] = hdr[5] = hdr[6] = hdr[7] = 0;
+  }
+  for (int i = tid; i < rows_alloc; i += blockDim.x) { pos[i] = -1; rem[i] = -1; utt[i] = -1; }
+  __syncthreads();
+  for (int b = 0; b < B; ++b) {
+    const int r0 = row0[b], l = len[b];
+    for (int t = tid; t < l; t += blockDim.x) { pos[r0 + t] = t; rem[r0 + t] = l - 1 - t; utt[r0 + t] = b; }
+  }
+}
+
+// ====================================================================================================
+// pack / unpack: (B, C, T) time-contiguous  <->  packed rows, channel-contiguous (32 x 32 smem transpose)
+// ====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, int C, int Tsrc, int g,
+                                                   PlanView pv, T* __restrict__ dst, int ld, int col_off,
+                                                   int ncols_pad) {
+  __shared__ float tile[32][33];
+  const int rows_used = pv.hdr()[0];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  if (r0 >= rows_used) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ncols = C * g;
+  {
+    const int row = r0 + tx;
+    const int b = row < pv.rows_alloc ? pv.utt()[row] : -1;
+    const int t = b >= 0 ? pv.pos()[row] : 0;
+    for (int cc = ty; cc < 32; cc += 8) {
+      const int col = c0 + cc;
+      float v = 0.f;
+      if (b >= 0 && col < ncols) {
+        const int c = col / g, k = col - c * g;
+        const int ts = g * t + k;
+        if (ts < Tsrc) v = src[((size_t)b * C + c) * Tsrc + ts];
+      }
+      tile[cc][tx] = v;
+    }
+  }
+  __syncthreads();
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int row = r0 + rr, col = c0 + tx;
+    if (row < pv.rows_alloc && col < ncols_pad) {
+      const float v = tile[tx][rr];
+      if (sizeof(T) == 4) reinterpret_cast<float*>(dst)[(size_t)row * ld + col_off + col] = v;
+      else reinterpret_cast<__nv_bfloat16*>(dst)[(size_t)row * ld + col_off + col] = __float2bfloat16(v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_kernel(const float* __restrict__ src, int ld, int col_off, PlanView pv,
+                                                     int C, int g, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ncols = C * g;
+  const int len = pv.len()[b], row0 = pv.row0()[b];
+  const int Tout = pv.Tmax * g;
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int t = t0 + rr, col = c0 + tx;
+    float v = 0.f;
+    if (t < len && col < ncols) v = src[(size_t)(row0 + t) * ld + col_off + col];
+    tile[rr][tx] = v;
+  }
+  __syncthreads();
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int col = c0 + cc, t = t0 + tx;
+    if (col < ncols && t < pv.Tmax) {
+      const int c = col / g, k = col - c * g;
+      dst[((size_t)b * C + c) * Tout + g * t + k] = tile[tx][cc];
+    }
+  }
+}
+
+// ====================================================================================================
+// weight re-layout kernels (run once per optimizer step / once per model)
+// ====================================================================================================
+template <typename T>
+__device__ __forceinline__ void put(T* p, float v);
+template <>
+__device__ __forceinline__ void put<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void put<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// conv weight (N, C, k) -> dst[n][t * C + c]  (tap-major K)
+template <typename T>
+__global__ void prep_conv_kernel(const float* __restrict__ w, int N, int C, int k, T* __restrict__ dst, int ldw) {
+  const size_t total = (size_t)N * C * k;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int t = (int)((i / C) % k);
+    const int n = (int)(i / ((size_t)C * k));
+    put(dst + (size_t)n * ldw + (size_t)t * C + c, w[((size_t)n * C + c) * k + t]);
+  }
+}
+// start weight (N, h + n_ctx) [z0 | ctx] -> dst[n][ctx (pad ctx_ld) | z0 (pad 128)]
+template <typename T>
+__global__ void prep_start_kernel(const float* __restrict__ w, int N, int h, int n_ctx, int ctx_ld,
+                                  T* __restrict__ dst) {
+  const int ldw = ctx_ld + 128;
+  const size_t total = (size_t)N * ldw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % ldw);
+    const int n = (int)(i / ldw);
+    float v = 0.f;
+    if (j < ctx_ld) { if (j < n_ctx) v = w[(size_t)n * (h + n_ctx) + h + j]; }
+    else if (j - ctx_ld < h) v = w[(size_t)n * (h + n_ctx) + (j - ctx_ld)];
+    put(dst + i, v);
+  }
+}
+// end weight (2h, n_ch) -> dst[2c + p][l * n_ch + k] replicated over the n_layers K blocks; rows >= 2h zero
+template <typename T>
+__global__ void prep_end_kernel(const float* __restrict__ w, const float* __restrict__ b, int h, int n_ch,
+                                int n_layers, int nrows, T* __restrict__ dst, float* __restrict__ bdst) {
+  const int ldw = n_layers * n_ch;
+  const size_t total = (size_t)nrows * ldw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % ldw);
+    const int r = (int)(i / ldw);
+    const int c = r >> 1, p = r & 1;
+    float v = 0.f;
+    if (c < h) v = w[(size_t)(p * h + c) * n_ch + (kk % n_ch)];
+    put(dst + i, v);
+    if (kk == 0) bdst[r] = c < h ? b[p * h + c] : 0.f;
+  }
+}
+// dst[col0_dst + r][...]: transposed window copy: dst[j][dcol + n] = src[n][scol + j], n < N, j < ncols
+template <typename T>
+__global__ void prep_transpose_kernel(const T* __restrict__ src, int lds, int scol, int N, int ncols,
+                                      T* __restrict__ dst, int ldd, int dcol) {
+  __shared__ T tile[32][33];
+  const int n0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int n = n0 + rr, j = j0 + tx;
+    if (n < N && j < ncols) tile[rr][tx] = src[(size_t)n * lds + scol + j];
+  }
+  __syncthreads();
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int j = j0 + rr, n = n0 + tx;
+    if (n < N && j < ncols) dst[(size_t)j * ldd + dcol + n] = tile[tx][rr];
+  }
+}
+template <typename T>
+__global__ void fill_zero_kernel(T* p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    put(p + i, 0.f);
+}
+// embeds W (C x C) into the z_ld x z_ld identity (exited channels pass through) and also writes its transpose
+__global__ void prep_inv_kernel(const float* __restrict__ w, int zld, int c_off, float* __restrict__ full,
+                                float* __restrict__ full_t) {
+  const int C = zld - c_off;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < zld * zld; i += gridDim.x * blockDim.x) {
+    const int r = i / zld, c = i % zld;
+    float v;
+    if (r >= c_off && c >= c_off) v = w[(size_t)(r - c_off) * C + (c - c_off)];
+    else v = (r == c) ? 1.f : 0.f;
+    full[(size_t)r * zld + c] = v;
+    if (full_t) full_t[(size_t)c * zld + r] = v;
+  }
+}
+__global__ void copy_f32_kernel(const float* __restrict__ s, float* __restrict__ d, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+// inverse direction prologue: z0 copy for `start`, and zmid[:, < c_off + h] = zin
+template <typename T>
+__global__ void extract_z0_kernel(const float* __restrict__ zin, int zld, int c_off, int h, const int* __restrict__ plan,
+                                  float* __restrict__ zmid, T* __restrict__ z0) {
+  const int rows_used = plan[0];
+  const size_t total = (size_t)rows_used * zld;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % zld);
+    const size_t row = i / zld;
+    const float v = zin[i];
+    if (c < c_off + h) zmid[i] = v;
+    if (c >= c_off && c < c_off + 128) put(z0 + row * 128 + (c - c_off), c < c_off + h ? v : 0.f);
+  }
+}
+
+static inline int grid_for(size_t n, int threads = 256) {
+  size_t b = (n + threads - 1) / threads;
+  if (b > (size_t)kNumSMs * 16) b = (size_t)kNumSMs * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ====================================================================================================
+// prepare
+// ====================================================================================================
+template <typename T>
+static int prepare_impl(const radtts_flow_dims& d, const radtts_flow_weights& w, int want_backward, uint8_t* base,
+                        const FlowLayout& L, cudaStream_t st) {
+  const int h = d.c_active / 2, nc = d.n_ch, k = d.ksize, nl = d.n_layers;
+  const int ldstart = L.ctx_ld + 128;
+  float* invf = reinterpret_cast<float*>(base + L.w_inv);
+  float* invt = want_backward ? reinterpret_cast<float*>(base + L.w_inv_t) : nullptr;
+  prep_inv_kernel<<<grid_for((size_t)d.z_ld * d.z_ld), 256, 0, st>>>(w.w_inv, d.z_ld, d.c_off, invf, invt);
+  RB_TRY(after_launch());
+  T* ws = reinterpret_cast<T*>(base + L.w_start);
+  prep_start_kernel<T><<<grid_for((size_t)nc * ldstart), 256, 0, st>>>(w.w_start, nc, h, d.n_ctx, L.ctx_ld, ws);
+  RB_TRY(after_launch());
+  copy_f32_kernel<<<grid_for(nc), 256, 0, st>>>(w.b_start, reinterpret_cast<float*>(base + L.b_start), nc);
+  RB_TRY(after_launch());
+  for (int i = 0; i < nl; ++i) {
+    prep_conv_kernel<T><<<grid_for((size_t)nc * nc * k), 256, 0, st>>>(w.w_in[i], nc, nc, k,
+                                                                      reinterpret_cast<T*>(base + L.w_in[i]), k * nc);
+    RB_TRY(after_launch());
+    prep_conv_kernel<T><<<grid_for((size_t)nc * nc), 256, 0, st>>>(w.w_rs[i], nc, nc, 1,
+                                                                  reinterpret_cast<T*>(base + L.w_rs[i]), nc);
+    RB_TRY(after_launch());
+    copy_f32_kernel<<<grid_for(nc), 256, 0, st>>>(w.b_in[i], reinterpret_cast<float*>(base + L.b_in[i]), nc);
+    RB_TRY(after_launch());
+    copy_f32_kernel<<<grid_for(nc), 256, 0, st>>>(w.b_rs[i], reinterpret_cast<float*>(base + L.b_rs[i]), nc);
+    RB_TRY(after_launch());
+  }
+  prep_end_kernel<T><<<grid_for((size_t)d.z_ld * nl * nc), 256, 0, st>>>(
+      w.w_end, w.b_end, h, nc, nl, d.z_ld, reinterpret_cast<T*>(base + L.w_end), reinterpret_cast<float*>(base + L.b_end));
+  RB_TRY(after_launch());
+  if (!want_backward) return 0;
+
+  auto transpose = [&](size_t src_off, int lds, int scol, int N, int ncols, size_t dst_off, int ldd, int dcol) -> int {
+    dim3 g(ceil_div(N, 32), ceil_div(ncols, 32));
+    prep_transpose_kernel<T><<<g, 256, 0, st>>>(reinterpret_cast<const T*>(base + src_off), lds, scol, N, ncols,
+                                                reinterpret_cast<T*>(base + dst_off), ldd, dcol);
+    return after_launch();
+  };
+  // end^T: [n_ch][end_kpad] (zero padded K) from the first K block of w_end
+  fill_zero_kernel<T><<<grid_for((size_t)nc * L.end_kpad), 256, 0, st>>>(reinterpret_cast<T*>(base + L.w_end_t),
+                                                                        (size_t)nc * L.end_kpad);
+  RB_TRY(after_launch());
+  RB_TRY(transpose(L.w_end, nl * nc, 0, d.z_ld, nc, L.w_end_t, L.end_kpad, 0));
+  // fused dgrad weights: layer i: [ rs_i^T | in_{i+1}^T taps ]
+  for (int i = 0; i < nl; ++i) {
+    const int ldd = L.dg_k[i];
+    RB_TRY(transpose(L.w_rs[i], nc, 0, nc, nc, L.w_dg[i], ldd, 0));
+    if (i + 1 < nl)
+      for (int t = 0; t < k; ++t) RB_TRY(transpose(L.w_in[i + 1], k * nc, t * nc, nc, nc, L.w_dg[i], ldd, nc + t * nc));
+  }
+  for (int t = 0; t < k; ++t) RB_TRY(transpose(L.w_in[0], k * nc, t * nc, nc, nc, L.w_dg0, k * nc, t * nc));
+  RB_TRY(transpose(L.w_start, ldstart, 0, nc, ldstart, L.w_start_t, nc, 0));
+  return 0;
+}
+
+// ====================================================================================================
+// forward / inverse
+// ====================================================================================================
+template <typename T, typename Epi>
+static int run_gemm(const GemmDesc& g, const Epi& e, cudaStream_t st) {
+  if (sizeof(T) == 4) return launch_rowgemm_simt(g, e, st);
+  return launch_rowgemm_tc(g, e, st);
+}
+
+template <typename T>
+static int wn_and_coupling(const radtts_flow_dims& d, const uint8_t* base, const FlowLayout& L, const PlanView& pv,
+                           const radtts_flow_buffers& buf, int inverse, cudaStream_t st) {
+  const int h = d.c_active / 2, nc = d.n_ch, k = d.ksize, nl = d.n_layers;
+  const int rows = pv.rows_alloc;
+  RowMeta meta{pv.pos(), pv.rem()};
+  T* x = reinterpret_cast<T*>(buf.x);
+  T* r = reinterpret_cast<T*>(buf.r);
+  GemmDesc g{};
+  g.rows_alloc = rows;
+  g.plan = pv.hdr();
+  // start
+  g.nseg = 2;
+  g.seg[0] = Seg{buf.ctx, L.ctx_ld, 0, 0, L.ctx_ld};
+  g.seg[1] = Seg{buf.z0, 128, 0, 0, 128};
+  g.w = base + L.w_start; g.ldw = L.ctx_ld + 128; g.N = nc;
+  {
+    EpiBiasAct<T> e{x, nc, 0, reinterpret_cast<const float*>(base + L.b_start), meta, ACT_NONE, 0, 0, k, 1};
+    RB_TRY((run_gemm<T>(g, e, st)));
+  }
+  for (int i = 0; i < nl; ++i) {
+    T* xi = x + (size_t)i * rows * nc;
+    T* xo = x + (size_t)(i + 1) * rows * nc;
+    g.nseg = k;
+    for (int t = 0; t < k; ++t) g.seg[t] = Seg{xi, nc, (t - k / 2) << i, 0, nc};
+    g.w = base + L.w_in[i]; g.ldw = k * nc; g.N = nc;
+    {
+      EpiBiasAct<T> e{xo, nc, 0, reinterpret_cast<const float*>(base + L.b_in[i]), meta, ACT_SOFTPLUS,
+                      d.partial_padding, i, k, 1};
+      RB_TRY((run_gemm<T>(g, e, st)));
+    }
+    g.nseg = 1;
+    g.seg[0] = Seg{xo, nc, 0, 0, nc};
+    g.w = base + L.w_rs[i]; g.ldw = nc; g.N = nc;
+    {
+      EpiBiasAct<T> e{r, nl * nc, i * nc, reinterpret_cast<const float*>(base + L.b_rs[i]), meta, ACT_SOFTPLUS, 0, 0, k, 1};
+      RB_TRY((run_gemm<T>(g, e, st)));
+    }
+  }
+  g.nseg = 1;
+  g.seg[0] = Seg{r, nl * nc, 0, 0, nl * nc};
+  g.w = base + L.w_end; g.ldw = nl * nc; g.N = d.z_ld;
+  {
+    EpiCoupling e{reinterpret_cast<const float*>(base + L.b_end), inverse ? buf.zin : buf.zmid,
+                  inverse ? buf.zmid : buf.zout, inverse ? nullptr : buf.log_s, inverse ? nullptr : buf.params,
+                  d.c_off, h, d.z_ld, inverse, d.scaling, meta};
+    RB_TRY((run_gemm<T>(g, e, st)));
+  }
+  return 0;
+}
+
+template <typename T>
+static int flowstep_impl(const radtts_flow_dims& d, const uint8_t* base, const PlanView& pv,
+                         const radtts_flow_buffers& buf, int inverse, cudaStream_t st) {
+  FlowLayout L = flow_layout(d, sizeof(T) == 4 ? RADTTS_PREC_FP32 : RADTTS_PREC_BF16, 0);
+  const int h = d.c_active / 2;
+  RowMeta meta{pv.pos(), pv.rem()};
+  GemmDesc g{};
+  g.rows_alloc = pv.rows_alloc;
+  g.plan = pv.hdr();
+  g.nseg = 1;
+  g.w = base + L.w_inv; g.ldw = d.z_ld; g.N = d.z_ld;
+  if (!inverse) {
+    g.seg[0] = Seg{buf.zin, d.z_ld, 0, 0, d.z_ld};
+    EpiInvConv<T> e{buf.zmid, buf.zout, reinterpret_cast<T*>(buf.z0), d.c_off, h, d.z_ld, meta};
+    RB_TRY(launch_rowgemm_simt(g, e, st));
+    return wn_and_coupling<T>(d, base, L, pv, buf, 0, st);
+  }
+  extract_z0_kernel<T><<<grid_for((size_t)pv.rows_alloc * d.z_ld), 256, 0, st>>>(
+      buf.zin, d.z_ld, d.c_off, h, pv.hdr(), buf.zmid, reinterpret_cast<T*>(buf.z0));
+  RB_TRY(after_launch());
+  RB_TRY(wn_and_coupling<T>(d, base, L, pv, buf, 1, st));
+  g.seg[0] = Seg{buf.zmid, d.z_ld, 0, 0, d.z_ld};
+  EpiStoreF32 e{buf.zout, d.z_ld, meta, 1};
+  return launch_rowgemm_simt(g, e, st);
+}
+
+static int check_dims(const radtts_flow_dims* d) {
+  if (!d) return RADTTS_ERR_INVALID_ARG;
+  if (d->z_ld <= 0 || d->z_ld % 16 || d->c_active <= 0 || d->c_active % 2 || d->c_off + d->c_active != d->z_ld)
+    return RADTTS_ERR_INVALID_ARG;
+  if (d->c_active / 2 > 128 || d->c_off + 128 > d->z_ld + 96) return RADTTS_ERR_UNSUPPORTED;
+  if (d->n_ch <= 0 || d->n_ch % 64 || d->n_layers < 1 || d->n_layers > RADTTS_MAX_LAYERS) return RADTTS_ERR_UNSUPPORTED;
+  if (d->ksize < 1 || d->ksize % 2 == 0 || d->ksize > kMaxSeg - 1 || d->n_ctx <= 0) return RADTTS_ERR_UNSUPPORTED;
+  if (((d->ksize / 2) << (d->n_layers - 1)) > kGap) return RADTTS_ERR_UNSUPPORTED;
+  return 0;
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" size_t radtts_frameplan_bytes(int B, int Tmax) {
+  if (B <= 0 || Tmax <= 0) return 0;
+  return plan_ints(B, Tmax) * sizeof(int);
+}
+extern "C" int radtts_frameplan_rows(int B, int Tmax) {
+  if (B <= 0 || Tmax <= 0) return 0;
+  return plan_rows_alloc(B, Tmax);
+}
+extern "C" int radtts_frameplan_build(const int64_t* lens, int divisor, int B, int Tmax, void* plan, void* stream) {
+  if (!lens || !plan || B <= 0 || Tmax <= 0 || divisor <= 0) return RADTTS_ERR_INVALID_ARG;
+  frameplan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lens, divisor, B, Tmax, plan_rows_alloc(B, Tmax),
+                                                        reinterpret_cast<int*>(plan));
+  return after_launch();
+}
+
+extern "C" int radtts_pack_frames(const float* src, int B, int C, int T, int g, const void* plan, int Tmax, void* dst,
+                                  int dst_bf16, int ld, int col_off, int ncols_pad, void* stream) {
+  if (!src || !plan || !dst || B <= 0 || C <= 0 || T <= 0 || g <= 0 || ncols_pad < C * g) return RADTTS_ERR_INVALID_ARG;
+  PlanView pv = make_plan_view(plan, B, Tmax);
+  dim3 grid(pv.rows_alloc / 32, ceil_div(ncols_pad, 32));
+  if (dst_bf16)
+    pack_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, C, T, g, pv, reinterpret_cast<__nv_bfloat16*>(dst),
+                                                                       ld, col_off, ncols_pad);
+  else
+    pack_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(src, C, T, g, pv, reinterpret_cast<float*>(dst), ld,
+                                                               col_off, ncols_pad);
+  return after_launch();
+}
+extern "C" int radtts_unpack_frames(const float* src, int ld, int col_off, const void* plan, int B, int Tmax, int C,
+                                    int g, float* dst, void* stream) {
+  if (!src || !plan || !dst || B <= 0 || C <= 0 || g <= 0) return RADTTS_ERR_INVALID_ARG;
+  PlanView pv = make_plan_view(plan, B, Tmax);
+  dim3 grid(ceil_div(Tmax, 32), ceil_div(C * g, 32), B);
+  unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld, col_off, pv, C, g, dst);
+  return after_launch();
+}
+
+extern "C" size_t radtts_flow_prepared_bytes(const radtts_flow_dims* dims, int precision, int want_backward) {
+  if (check_dims(dims)) return 0;
+  return flow_layout(*dims, precision, want_backward).total;
+}
+extern "C" int radtts_flow_prepare(const radtts_flow_dims* dims, const radtts_flow_weights* w, int inverse,
+                                   int precision, int want_backward, void* prepared, size_t prepared_bytes,
+                                   void* stream) {
+  (void)inverse;  // the caller passes W or W^-1 in w_inv; nothing else depends on the direction
+  RB_TRY(check_dims(dims));
+  if (!w || !prepared) return RADTTS_ERR_INVALID_ARG;
+  FlowLayout L = flow_layout(*dims, precision, want_backward);
+  if (prepared_bytes < L.total) return RADTTS_ERR_WORKSPACE;
+  if (precision == RADTTS_PREC_FP32)
+    return prepare_impl<float>(*dims, *w, want_backward, reinterpret_cast<uint8_t*>(prepared), L, (cudaStream_t)stream);
+  if (precision == RADTTS_PREC_BF16)
+    return prepare_impl<__nv_bfloat16>(*dims, *w, want_backward, reinterpret_cast<uint8_t*>(prepared), L,
+                                       (cudaStream_t)stream);
+  return RADTTS_ERR_INVALID_ARG;
+}
+
+static int flowstep_entry(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B, int Tmax,
+                          const radtts_flow_buffers* buf, int precision, int inverse, void* stream) {
+  RB_TRY(check_dims(dims));
+  if (!prepared || !plan || !buf || B <= 0 || Tmax <= 0) return RADTTS_ERR_INVALID_ARG;
+  if (!buf->ctx || !buf->zin || !buf->zmid || !buf->zout || !buf->z0 || !buf->x || !buf->r) return RADTTS_ERR_INVALID_ARG;
+  if (!inverse && !buf->log_s) return RADTTS_ERR_INVALID_ARG;
+  PlanView pv = make_plan_view(plan, B, Tmax);
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(prepared);
+  if (precision == RADTTS_PREC_FP32) return flowstep_impl<float>(*dims, base, pv, *buf, inverse, (cudaStream_t)stream);
+  if (precision == RADTTS_PREC_BF16)
+    return flowstep_impl<__nv_bfloat16>(*dims, base, pv, *buf, inverse, (cudaStream_t)stream);
+  return RADTTS_ERR_INVALID_ARG;
+}
+extern "C" int radtts_flowstep_forward(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
+                                       int Tmax, const radtts_flow_buffers* buf, int precision, void* stream) {
+  return flowstep_entry(dims, prepared, plan, B, Tmax, buf, precision, 0, stream);
+}
+extern "C" int radtts_flowstep_inverse(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
+                                       int Tmax, const radtts_flow_buffers* buf, int precision, void* stream) {
+  return flowstep_entry(dims, prepared, plan, B, Tmax, buf, precision, 1, stream);
+}

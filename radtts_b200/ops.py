@@ -1,0 +1,389 @@
+"""Bridge between the reference-shaped nn.Modules and the C-ABI CUDA library.
+
+Everything here is plumbing: tensor allocation, ctypes structs, autograd.Function wrappers and the packed
+frame-plan bookkeeping.  All math of the hot path happens inside libradtts_b200.so; if the library is
+missing or an input is not on a CUDA device these functions raise (no CPU fallback).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+PREC_FP32, PREC_BF16 = 0, 1
+MAX_LAYERS = 8
+_SCALING = {"tanh": 0, "exp": 1, "sigmoid": 2, "translate": 3}
+
+_forced_precision = None
+
+
+def set_precision(p):
+    """None: follow torch autocast (bf16 inside autocast, fp32 otherwise); 'fp32' / 'bf16': force."""
+    global _forced_precision
+    assert p in (None, "fp32", "bf16")
+    _forced_precision = p
+
+
+def current_precision():
+    if _forced_precision is not None:
+        return PREC_BF16 if _forced_precision == "bf16" else PREC_FP32
+    return PREC_BF16 if torch.is_autocast_enabled() else PREC_FP32
+
+
+def _act_dtype(prec):
+    return torch.bfloat16 if prec == PREC_BF16 else torch.float32
+
+
+# ------------------------------------------------------------------------------------------------------
+# ctypes mirrors of the public structs
+# ------------------------------------------------------------------------------------------------------
+class FlowDims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("z_ld", "c_off", "c_active", "n_ctx", "n_ch", "n_layers", "ksize", "partial_padding", "scaling")]
+
+
+_P = ctypes.c_void_p
+
+
+class FlowWeights(ctypes.Structure):
+    _fields_ = [("w_inv", _P), ("w_start", _P), ("b_start", _P), ("w_in", _P * MAX_LAYERS), ("b_in", _P * MAX_LAYERS),
+                ("w_rs", _P * MAX_LAYERS), ("b_rs", _P * MAX_LAYERS), ("w_end", _P), ("b_end", _P)]
+
+
+class FlowBuffers(ctypes.Structure):
+    _fields_ = [(n, _P) for n in ("ctx", "zin", "zmid", "zout", "z0", "x", "r", "params", "log_s")]
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------------
+# plain data movement used by the module API (views, no kernels needed)
+# ------------------------------------------------------------------------------------------------------
+def squeeze_time(x, g):
+    """z[b, c*g+k, t'] = x[b, c, g*t'+k]  (reference nn.Unfold((g,1), stride g), radtts.py:165-169)."""
+    b, c, t = x.shape
+    tt = t // g
+    return x[:, :, :tt * g].reshape(b, c, tt, g).permute(0, 1, 3, 2).reshape(b, c * g, tt)
+
+
+def unsqueeze_time(z, g):
+    b, cg, tt = z.shape
+    return z.reshape(b, cg // g, g, tt).permute(0, 1, 3, 2).reshape(b, cg // g, tt * g)
+
+
+# ------------------------------------------------------------------------------------------------------
+# frame plan + pack / unpack
+# ------------------------------------------------------------------------------------------------------
+class FramePlan:
+    """Device-side description of the packed frame layout (see csrc/frameplan.cuh)."""
+
+    def __init__(self, lens, divisor, tmax):
+        _lib.require_cuda(lens)
+        L = _lib.lib()
+        self.B = int(lens.shape[0])
+        self.Tmax = int(tmax)
+        self.divisor = int(divisor)
+        self.rows = int(L.radtts_frameplan_rows(self.B, self.Tmax))
+        nbytes = int(L.radtts_frameplan_bytes(self.B, self.Tmax))
+        self.buf = torch.empty(nbytes // 4, dtype=torch.int32, device=lens.device)
+        self.lens = lens.to(torch.int64).contiguous()
+        _lib.check(L.radtts_frameplan_build(_lib.ptr(self.lens), self.divisor, self.B, self.Tmax,
+                                            _lib.ptr(self.buf), _lib.stream_of(lens)), "radtts_frameplan_build")
+
+    @property
+    def ptr(self):
+        return _lib.ptr(self.buf)
+
+    def frame_lens(self):
+        return torch.div(self.lens, self.divisor, rounding_mode="floor").clamp(0, self.Tmax)
+
+
+def pack_frames(src, plan, g, dtype=torch.float32, ld=None, col_off=0, ncols_pad=None, out=None):
+    """(B, C, T) fp32 -> packed [rows][ld]; columns [col_off, col_off + ncols_pad) are written."""
+    _lib.require_cuda(src)
+    src = src.float().contiguous()
+    B, C, T = src.shape
+    ncols = C * g
+    ncols_pad = ncols if ncols_pad is None else ncols_pad
+    ld = col_off + ncols_pad if ld is None else ld
+    if out is None:
+        out = torch.zeros((plan.rows, ld), dtype=dtype, device=src.device) if ld != col_off + ncols_pad or col_off \
+            else torch.empty((plan.rows, ld), dtype=dtype, device=src.device)
+    L = _lib.lib()
+    _lib.check(L.radtts_pack_frames(_lib.ptr(src), B, C, T, g, plan.ptr, plan.Tmax, _lib.ptr(out),
+                                    int(out.dtype == torch.bfloat16), ld, col_off, ncols_pad, _lib.stream_of(src)),
+               "radtts_pack_frames")
+    return out
+
+
+def unpack_frames(packed, plan, C, g, col_off=0):
+    """packed fp32 [rows][ld] -> (B, C, Tmax*g) fp32 (zeros beyond each utterance)."""
+    _lib.require_cuda(packed)
+    assert packed.dtype == torch.float32 and packed.is_contiguous()
+    out = torch.empty((plan.B, C, plan.Tmax * g), dtype=torch.float32, device=packed.device)
+    L = _lib.lib()
+    _lib.check(L.radtts_unpack_frames(_lib.ptr(packed), packed.shape[1], col_off, plan.ptr, plan.B, plan.Tmax, C, g,
+                                      _lib.ptr(out), _lib.stream_of(packed)), "radtts_unpack_frames")
+    return out
+
+
+class _PackFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, plan, g, dtype, ld, col_off, ncols_pad):
+        ctx.plan, ctx.g, ctx.col_off, ctx.C = plan, g, col_off, src.shape[1]
+        ctx.T = src.shape[2]
+        return pack_frames(src, plan, g, dtype, ld, col_off, ncols_pad)
+
+    @staticmethod
+    def backward(ctx, grad):
+        g = unpack_frames(grad.float().contiguous(), ctx.plan, ctx.C, ctx.g, ctx.col_off)
+        if g.shape[2] != ctx.T:
+            g = torch.nn.functional.pad(g, (0, ctx.T - g.shape[2])) if g.shape[2] < ctx.T else g[:, :, :ctx.T]
+        return g, None, None, None, None, None, None
+
+
+class _UnpackFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, packed, plan, C, g, col_off):
+        ctx.plan, ctx.g, ctx.col_off, ctx.ld, ctx.C = plan, g, col_off, packed.shape[1], C
+        return unpack_frames(packed, plan, C, g, col_off)
+
+    @staticmethod
+    def backward(ctx, grad):
+        out = pack_frames(grad.contiguous(), ctx.plan, ctx.g, torch.float32, ctx.ld, ctx.col_off, ctx.C * ctx.g)
+        return out, None, None, None, None
+
+
+def pack(src, plan, g=1, dtype=torch.float32, ld=None, col_off=0, ncols_pad=None):
+    return _PackFn.apply(src, plan, g, dtype, ld, col_off, ncols_pad)
+
+
+def unpack(packed, plan, C, g=1, col_off=0):
+    return _UnpackFn.apply(packed, plan, C, g, col_off)
+
+
+# ------------------------------------------------------------------------------------------------------
+# flow step
+# ------------------------------------------------------------------------------------------------------
+def _effective(conv):
+    """Weight of a (possibly weight-normed) conv: w = g * v / ||v|| (torch.nn.utils.weight_norm, dim 0)."""
+    if hasattr(conv, "weight_v"):
+        return torch._weight_norm(conv.weight_v, conv.weight_g, 0)
+    return conv.weight
+
+
+def _flow_dims(flow, z_ld, c_active):
+    wn = flow.affine_tfn.affine_param_predictor
+    scaling = flow.affine_tfn.scaling_fn
+    if isinstance(scaling, list) or scaling not in _SCALING:
+        raise NotImplementedError("per-channel scaling_fn lists are outside the fused flow-step kernel")
+    return FlowDims(z_ld=z_ld, c_off=z_ld - c_active, c_active=c_active, n_ctx=wn.n_context_dim, n_ch=wn.n_channels,
+                    n_layers=wn.n_layers, ksize=wn.kernel_size, partial_padding=int(wn.use_partial_padding),
+                    scaling=_SCALING[scaling])
+
+
+def _flow_weight_list(flow, inverse):
+    """Flat list of effective fp32 weights, in the order FlowWeights expects."""
+    wn = flow.affine_tfn.affine_param_predictor
+    inv = flow.invtbl_conv
+    if hasattr(inv, "lower"):
+        w_inv = inv.inverse_weight() if inverse else inv.weight()
+    else:
+        w_inv = inv.inverse_weight() if inverse else inv.conv.weight.squeeze(-1)
+    ws = [w_inv.float(), _effective(wn.start).squeeze(-1), wn.start.bias]
+    for i in range(wn.n_layers):
+        ws += [_effective(wn.in_layers[i].conv), wn.in_layers[i].conv.bias]
+    for i in range(wn.n_layers):
+        ws += [_effective(wn.res_skip_layers[i]).squeeze(-1), wn.res_skip_layers[i].bias]
+    ws += [wn.end.weight.squeeze(-1), wn.end.bias]
+    return ws
+
+
+def _weights_struct(ws, n_layers):
+    ws = [w.detach().float().contiguous() for w in ws]
+    s = FlowWeights()
+    s.w_inv, s.w_start, s.b_start = _p(ws[0]), _p(ws[1]), _p(ws[2])
+    for i in range(n_layers):
+        s.w_in[i], s.b_in[i] = _p(ws[3 + 2 * i]), _p(ws[4 + 2 * i])
+        s.w_rs[i], s.b_rs[i] = _p(ws[3 + 2 * n_layers + 2 * i]), _p(ws[4 + 2 * n_layers + 2 * i])
+    s.w_end, s.b_end = _p(ws[3 + 4 * n_layers]), _p(ws[4 + 4 * n_layers])
+    return s, ws  # keep `ws` alive until the prepare kernels have been enqueued on the stream
+
+
+def prepare_flow(dims, ws, prec, want_backward, device):
+    L = _lib.lib()
+    nbytes = int(L.radtts_flow_prepared_bytes(ctypes.byref(dims), prec, int(want_backward)))
+    if nbytes == 0:
+        raise _lib.RadttsB200Error("unsupported flow-step dimensions for the CUDA kernels")
+    blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    s, keep = _weights_struct(ws, dims.n_layers)
+    _lib.check(L.radtts_flow_prepare(ctypes.byref(dims), ctypes.byref(s), 0, prec, int(want_backward),
+                                     _lib.ptr(blob), ctypes.c_size_t(nbytes),
+                                     ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+               "radtts_flow_prepare")
+    return blob
+
+
+def _alloc_buffers(dims, plan, prec, device, zin, ctx_packed):
+    act = _act_dtype(prec)
+    rows = plan.rows
+    b = {
+        "zmid": torch.empty((rows, dims.z_ld), dtype=torch.float32, device=device),
+        "zout": torch.zeros((rows, dims.z_ld), dtype=torch.float32, device=device),
+        "z0": torch.empty((rows, 128), dtype=act, device=device),
+        "x": torch.empty((dims.n_layers + 1, rows, dims.n_ch), dtype=act, device=device),
+        "r": torch.empty((rows, dims.n_layers * dims.n_ch), dtype=act, device=device),
+        "params": torch.empty((rows, dims.z_ld), dtype=torch.float32, device=device),
+        "log_s": torch.zeros((rows, dims.z_ld // 2), dtype=torch.float32, device=device),
+    }
+    s = FlowBuffers(ctx=_p(ctx_packed), zin=_p(zin), zmid=_p(b["zmid"]), zout=_p(b["zout"]), z0=_p(b["z0"]),
+                    x=_p(b["x"]), r=_p(b["r"]), params=_p(b["params"]), log_s=_p(b["log_s"]))
+    return b, s
+
+
+def run_flowstep(dims, blob, plan, zin, ctx_packed, prec, inverse):
+    """zin fp32 [rows][z_ld], ctx_packed act [rows][ctx_ld].  Returns (zout, log_s or None, buffers)."""
+    dev = zin.device
+    bufs, s = _alloc_buffers(dims, plan, prec, dev, zin, ctx_packed)
+    L = _lib.lib()
+    fn = L.radtts_flowstep_inverse if inverse else L.radtts_flowstep_forward
+    _lib.check(fn(ctypes.byref(dims), _lib.ptr(blob), plan.ptr, plan.B, plan.Tmax, ctypes.byref(s), prec,
+                  ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+               "radtts_flowstep_inverse" if inverse else "radtts_flowstep_forward")
+    return bufs["zout"], (None if inverse else bufs["log_s"]), bufs
+
+
+class _FlowStepFn(torch.autograd.Function):
+    """One decoder flow on packed rows.  inputs: zin [rows][z_ld] fp32, ctx [rows][ctx_ld] act, then the
+    effective weights (so that weight-norm / LUS parameter gradients are left to autograd)."""
+
+    @staticmethod
+    def forward(ctx, zin, ctx_packed, plan, dims, prec, inverse, *ws):
+        need_bwd = (not inverse) and any(t.requires_grad for t in (zin, ctx_packed) + tuple(ws))
+        blob = prepare_flow(dims, ws, prec, need_bwd, zin.device)
+        zout, log_s, bufs = run_flowstep(dims, blob, plan, zin.contiguous(), ctx_packed, prec, inverse)
+        if need_bwd:
+            ctx.saved = (zin, ctx_packed, plan, dims, prec, blob, bufs, [w.shape for w in ws])
+        if inverse:
+            return zout
+        return zout, log_s
+
+    @staticmethod
+    def backward(ctx, g_zout, g_log_s=None):
+        from . import ops_backward
+        return ops_backward.flowstep_backward(ctx.saved, g_zout, g_log_s)
+
+
+def ctx_ld_of(n_ctx):
+    return (n_ctx + 63) // 64 * 64
+
+
+def flow_step_packed(flow, zin, ctx_packed, plan, z_ld, c_active, inverse=False, prec=None):
+    prec = current_precision() if prec is None else prec
+    dims = _flow_dims(flow, z_ld, c_active)
+    ws = _flow_weight_list(flow, inverse)
+    out = _FlowStepFn.apply(zin, ctx_packed, plan, dims, prec, inverse, *ws)
+    if inverse:
+        return out
+    zout, log_s = out
+    inv = flow.invtbl_conv
+    log_det = inv.log_det() if hasattr(inv, "log_det") else torch.logdet(inv.conv.weight.squeeze(-1)).clone()
+    return zout, log_det, log_s
+
+
+def _is_fused_flow(flow):
+    wn = getattr(flow.affine_tfn, "affine_param_predictor", None)
+    return flow.affine_tfn.affine_model == "wavenet" and wn is not None and wn.affine_activation == "softplus"
+
+
+def flow_step(flow, z, context, inverse=False, seq_lens=None):
+    """FlowStep.forward on reference-shaped tensors: z (B,C,T'), context (B,n_ctx,T')."""
+    _lib.require_cuda(z, context)
+    if not _is_fused_flow(flow):
+        raise NotImplementedError("decoder FlowStep supports affine_model='wavenet' with softplus activations")
+    B, C, T = z.shape
+    if seq_lens is None:
+        seq_lens = torch.full((B,), T, dtype=torch.int64, device=z.device)
+    prec = current_precision()
+    plan = FramePlan(seq_lens.to(z.device), 1, T)
+    z_ld = (C + 15) // 16 * 16
+    n_ctx = context.shape[1]
+    zin = pack(z, plan, 1, torch.float32, z_ld, z_ld - C, C)
+    ctxp = pack(context, plan, 1, _act_dtype(prec), ctx_ld_of(n_ctx), 0, ctx_ld_of(n_ctx))
+    if inverse:
+        zout = flow_step_packed(flow, zin, ctxp, plan, z_ld, C, True, prec)
+        return unpack(zout, plan, C, 1, z_ld - C)
+    zout, log_det, log_s = flow_step_packed(flow, zin, ctxp, plan, z_ld, C, False, prec)
+    return unpack(zout, plan, C, 1, z_ld - C), log_det, unpack(log_s, plan, C // 2, 1, 0)
+
+
+def decoder_forward(model, mel, context, out_lens):
+    """Training direction of the decoder loop (reference radtts.py:414,431-444) on packed frames: one pack,
+    n_flows fused flow steps operating in place on the column suffix that is still active, one unpack."""
+    _lib.require_cuda(mel, context)
+    g = model.n_group_size
+    prec = current_precision()
+    z_ld = model.n_mel_channels * g
+    plan = FramePlan(out_lens.to(mel.device), g, mel.shape[2] // g)
+    z = pack(mel, plan, g, torch.float32, z_ld, 0, z_ld)
+    n_ctx = context.shape[1]
+    ctxp = pack(context, plan, 1, _act_dtype(prec), ctx_ld_of(n_ctx), 0, ctx_ld_of(n_ctx))
+    log_s_list, log_det_list = [], []
+    c_active = z_ld
+    for i, flow in enumerate(model.flows):
+        if i in model.exit_steps:
+            c_active -= model.n_early_size
+        z, log_det, log_s = flow_step_packed(flow, z, ctxp, plan, z_ld, c_active, False, prec)
+        log_det_list.append(log_det)
+        log_s_list.append(unpack(log_s, plan, c_active // 2, 1, 0))
+    return unpack(z, plan, z_ld, 1, 0), log_det_list, log_s_list
+
+
+def decoder_inverse(model, residual, context, out_lens):
+    """Sampling direction (reference radtts.py:656-677): residual (B, 80*g, T') -> mel (B, 80, T'*g)."""
+    _lib.require_cuda(residual, context)
+    g = model.n_group_size
+    prec = current_precision()
+    z_ld = residual.shape[1]
+    plan = FramePlan(out_lens.to(residual.device), g, residual.shape[2])
+    z = pack(residual, plan, 1, torch.float32, z_ld, 0, z_ld)
+    n_ctx = context.shape[1]
+    ctxp = pack(context, plan, 1, _act_dtype(prec), ctx_ld_of(n_ctx), 0, ctx_ld_of(n_ctx))
+    actives = []
+    c_active = z_ld
+    for i in range(len(model.flows)):
+        if i in model.exit_steps:
+            c_active -= model.n_early_size
+        actives.append(c_active)
+    for i in reversed(range(len(model.flows))):
+        z = flow_step_packed(model.flows[i], z, ctxp, plan, z_ld, actives[i], True, prec)
+    return unpack(z, plan, z_ld // g, g, 0)
+
+
+# ------------------------------------------------------------------------------------------------------
+# remaining hot-path entry points (filled in as their kernels land)
+# ------------------------------------------------------------------------------------------------------
+def pointwise_conv(z, w):
+    raise NotImplementedError
+
+
+def wn_forward(wn, z, context, seq_lens):
+    raise NotImplementedError("WN runs fused inside FlowStep (ops.flow_step); standalone WN.forward is not exposed")
+
+
+def affine_coupling(layer, z, context, inverse, seq_lens):
+    raise NotImplementedError
+
+
+def simple_conv_net(net, x, seq_lens):
+    raise NotImplementedError
+
+
+def spline_coupling(layer, z, context, inverse, seq_lens):
+    raise NotImplementedError
+
+
+def conv_attention(att, queries, keys, mask, key_lens, attn_prior):
+    raise NotImplementedError
