@@ -282,8 +282,8 @@ static int prepare_impl(const radtts_flow_dims& d, const radtts_flow_weights& w,
 // ====================================================================================================
 template <typename T, typename Epi>
 static int run_gemm(const GemmDesc& g, const Epi& e, cudaStream_t st) {
-  if (sizeof(T) == 4) return launch_rowgemm_simt(g, e, st);
-  return launch_rowgemm_tc(g, e, st);
+  if constexpr (sizeof(T) == 4) return launch_rowgemm_simt(g, e, st);
+  else return launch_rowgemm_tc(g, e, st);
 }
 
 template <typename T>

@@ -94,6 +94,17 @@ struct Act<__nv_bfloat16> {
 __device__ __forceinline__ float softplus20(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 // d softplus / dx expressed through the OUTPUT y = softplus(x):  sigmoid(x) = 1 - exp(-y)
 __device__ __forceinline__ float softplus_grad_from_out(float y) { return 1.f - expf(-y); }
+// bf16 path: MUFU-based versions (their ~1e-6 error is far below the bf16 rounding of the stored result)
+__device__ __forceinline__ float softplus20_fast(float x) {
+  return x > 20.f ? x : fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x)));
+}
+__device__ __forceinline__ float softplus_grad_from_out_fast(float y) { return 1.f - __expf(-y); }
+template <typename T>
+__device__ __forceinline__ float softplus_t(float x) { return sizeof(T) == 2 ? softplus20_fast(x) : softplus20(x); }
+template <typename T>
+__device__ __forceinline__ float softplus_grad_t(float y) {
+  return sizeof(T) == 2 ? softplus_grad_from_out_fast(y) : softplus_grad_from_out(y);
+}
 
 // Row validity + partial-conv renormalisation (reference partialconv1d.py:51-56): for a frame at position
 // `pos` of an utterance with `rem` frames after it, a k-tap conv with dilation 2^log2d sees
@@ -134,7 +145,7 @@ struct EpiBiasAct {
 #pragma unroll
     for (int i = 0; i < W; ++i) {
       float v = acc[i] * rt + bias[col0 + i];
-      if (act == ACT_SOFTPLUS) v = softplus20(v);
+      if (act == ACT_SOFTPLUS) v = softplus_t<T>(v);
       else if (act == ACT_RELU) v = fmaxf(v, 0.f);
       y[i] = ok ? v : 0.f;
     }
@@ -240,7 +251,7 @@ struct EpiEndDgrad {
       float rv[W], y[W];
       Act<T>::template ldv<W>(r + (size_t)row * ldr + l * n_ch + col0, rv);
 #pragma unroll
-      for (int i = 0; i < W; ++i) y[i] = ok ? acc[i] * softplus_grad_from_out(rv[i]) : 0.f;
+      for (int i = 0; i < W; ++i) y[i] = ok ? acc[i] * softplus_grad_t<T>(rv[i]) : 0.f;
       Act<T>::template stv<W>(gu + ((size_t)l * rows_alloc + row) * n_ch + col0, y);
     }
   }
@@ -263,7 +274,7 @@ struct EpiDgradAct {
       if (act == ACT_SOFTPLUS) Act<T>::template ldv<W>(x + (size_t)row * ldx + col0, xv);
       const float rt = partial ? meta.ratio(row, log2d, ksize) : 1.f;
 #pragma unroll
-      for (int i = 0; i < W; ++i) y[i] = acc[i] * (act == ACT_SOFTPLUS ? softplus_grad_from_out(xv[i]) : 1.f) * rt;
+      for (int i = 0; i < W; ++i) y[i] = acc[i] * (act == ACT_SOFTPLUS ? softplus_grad_t<T>(xv[i]) : 1.f) * rt;
     } else {
 #pragma unroll
       for (int i = 0; i < W; ++i) y[i] = 0.f;
