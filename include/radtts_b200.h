@@ -154,6 +154,34 @@ RADTTS_API int radtts_flowstep_forward(const radtts_flow_dims* dims, const void*
 RADTTS_API int radtts_flowstep_inverse(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
                                        int Tmax, const radtts_flow_buffers* buf, int precision, void* stream);
 
+/* Backward of radtts_flowstep_forward (what PyTorch autograd derives for the reference).
+ * Consumes the activation buffers the forward call filled (`fwd`) and a prepared blob built with
+ * want_backward = 1.  Weight gradients are float32 in the reference's PyTorch layouts and are OVERWRITTEN. */
+typedef struct radtts_flow_grad_buffers {
+  const float* g_zout;  /* [rows][z_ld] dL/d zout */
+  const float* g_log_s; /* [rows][z_ld/2] dL/d log_s (NULL = zeros) */
+  float* g_zin;         /* [rows][z_ld] out */
+  float* g_ctx;         /* [rows][ctx_ld] out, float32; += when accumulate_ctx */
+  float* g_zmid;        /* scratch [rows][z_ld] */
+  void* g_params;       /* scratch act [rows][round_up(z_ld, 64)] */
+  void* g_u;            /* scratch act [n_layers][rows][n_ch] */
+  void* g_v;            /* scratch act [n_layers][rows][n_ch] */
+  void* g_x0;           /* scratch act [rows][n_ch] */
+  float* g_w_inv_full;  /* out [z_ld][z_ld]: gradient of the identity-embedded 1x1 matrix (active block = dL/dW) */
+  float* g_w_start;     /* out (n_ch, h + n_ctx) */
+  float* g_b_start;
+  float* g_w_in[RADTTS_MAX_LAYERS]; /* out TAP-MAJOR (ksize, n_ch, n_ch): [t][out][in]; permute(1,2,0) = reference layout */
+  float* g_b_in[RADTTS_MAX_LAYERS];
+  float* g_w_rs[RADTTS_MAX_LAYERS]; /* out (n_ch, n_ch) */
+  float* g_b_rs[RADTTS_MAX_LAYERS];
+  float* g_w_end;       /* out (2h, n_ch) */
+  float* g_b_end;       /* out (2h) */
+  float* scratch_f32;   /* scratch [z_ld][n_ch + 1] */
+} radtts_flow_grad_buffers;
+RADTTS_API int radtts_flowstep_backward(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
+                                        int Tmax, const radtts_flow_buffers* fwd, const radtts_flow_grad_buffers* g,
+                                        int accumulate_ctx, int precision, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "flow_common.cuh"
 #include "flow_layout.cuh"
 #include "frameplan.cuh"
 #include "rowgemm.cuh"
@@ -51,9 +52,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src
                                                    PlanView pv, T* __restrict__ dst, int ld, int col_off,
                                                    int ncols_pad) {
   __shared__ float tile[32][33];
-  const int rows_used = pv.hdr()[0];
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  if (r0 >= rows_used) return;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;  // all rows_alloc rows are written (zeros off-range)
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int ncols = C * g;
   {
@@ -213,13 +212,6 @@ __global__ void extract_z0_kernel(const float* __restrict__ zin, int zld, int c_
   }
 }
 
-static inline int grid_for(size_t n, int threads = 256) {
-  size_t b = (n + threads - 1) / threads;
-  if (b > (size_t)kNumSMs * 16) b = (size_t)kNumSMs * 16;
-  if (b < 1) b = 1;
-  return (int)b;
-}
-
 // ====================================================================================================
 // prepare
 // ====================================================================================================
@@ -280,12 +272,6 @@ static int prepare_impl(const radtts_flow_dims& d, const radtts_flow_weights& w,
 // ====================================================================================================
 // forward / inverse
 // ====================================================================================================
-template <typename T, typename Epi>
-static int run_gemm(const GemmDesc& g, const Epi& e, cudaStream_t st) {
-  if constexpr (sizeof(T) == 4) return launch_rowgemm_simt(g, e, st);
-  else return launch_rowgemm_tc(g, e, st);
-}
-
 template <typename T>
 static int wn_and_coupling(const radtts_flow_dims& d, const uint8_t* base, const FlowLayout& L, const PlanView& pv,
                            const radtts_flow_buffers& buf, int inverse, cudaStream_t st) {
@@ -361,17 +347,6 @@ static int flowstep_impl(const radtts_flow_dims& d, const uint8_t* base, const P
   g.seg[0] = Seg{buf.zmid, d.z_ld, 0, 0, d.z_ld};
   EpiStoreF32 e{buf.zout, d.z_ld, meta, 1};
   return launch_rowgemm_simt(g, e, st);
-}
-
-static int check_dims(const radtts_flow_dims* d) {
-  if (!d) return RADTTS_ERR_INVALID_ARG;
-  if (d->z_ld <= 0 || d->z_ld % 16 || d->c_active <= 0 || d->c_active % 2 || d->c_off + d->c_active != d->z_ld)
-    return RADTTS_ERR_INVALID_ARG;
-  if (d->c_active / 2 > 128 || d->c_off + 128 > d->z_ld + 96) return RADTTS_ERR_UNSUPPORTED;
-  if (d->n_ch <= 0 || d->n_ch % 64 || d->n_layers < 1 || d->n_layers > RADTTS_MAX_LAYERS) return RADTTS_ERR_UNSUPPORTED;
-  if (d->ksize < 1 || d->ksize % 2 == 0 || d->ksize > kMaxSeg - 1 || d->n_ctx <= 0) return RADTTS_ERR_UNSUPPORTED;
-  if (((d->ksize / 2) << (d->n_layers - 1)) > kGap) return RADTTS_ERR_UNSUPPORTED;
-  return 0;
 }
 
 }  // namespace rb

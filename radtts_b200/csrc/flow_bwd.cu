@@ -1,0 +1,239 @@
+// Kernel 2, backward direction: everything PyTorch autograd derives for one reference FlowStep
+// (SURVEY Appendix C), as explicit kernels on the packed frame layout.
+//   1. coupling backward (elementwise)            -> g_params, g_zmid[z1]
+//   2. `end` dgrad GEMM, epilogue emits g_u_i = g_R * softplus'(r_i) for all layers
+//   3. per layer, ONE fused dgrad GEMM: g_x_{i+1} = g_u_i W_rs_i + convT(g_v_{i+1}); epilogue applies
+//      softplus' and the partial-conv ratio -> g_v_i
+//   4. convT(g_v_0) -> g_x0;  `start` dgrad -> g_ctx (+= over flows), g_zmid[z0] +=
+//   5. 1x1-conv dgrad (fp32) -> g_zin
+//   6. weight gradients: wgrad GEMMs (K = packed rows) + bias column sums
+#include <cuda_bf16.h>
+
+#include "flow_common.cuh"
+#include "wgrad.cuh"
+
+namespace rb {
+
+template <typename T>
+__device__ __forceinline__ void put_act(T* p, float v);
+template <>
+__device__ __forceinline__ void put_act<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void put_act<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// ----------------------------------------------------------------------------------------------------
+// 1. coupling backward.  z1' = s z1 + b, log_s = log s, s = f(x):
+//      g_z1 = s g_z1',  g_b = g_z1',  g_x = (g_z1' z1 + g_log_s / s) ds/dx
+//    also seeds g_zmid with the pass-through columns (exited channels and z0).
+// ----------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restrict__ g_zout, const float* __restrict__ g_log_s,
+                                                           const float* __restrict__ params, const float* __restrict__ zmid,
+                                                           RowMeta meta, const int* __restrict__ plan, int zld, int c_off,
+                                                           int h, int scaling, int kpad, float* __restrict__ g_zmid,
+                                                           T* __restrict__ g_params) {
+  const int rows_used = (plan[0] + 127) / 128 * 128;  // whole tiles: rows past the packed range get zeros
+  const int per_row = kpad > zld ? kpad : zld;
+  const size_t total = (size_t)rows_used * per_row;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % per_row);
+    const int row = (int)(i / per_row);
+    const bool ok = meta.valid(row);
+    // pass-through part of g_zmid
+    if (j < c_off + h) g_zmid[(size_t)row * zld + j] = ok ? g_zout[(size_t)row * zld + j] : 0.f;
+    if (j < kpad) {
+      float gp = 0.f;
+      const int c = j >> 1, which = j & 1;
+      if (!ok && c < h && !which) g_zmid[(size_t)row * zld + c_off + h + c] = 0.f;
+      if (ok && c < h) {
+        const size_t zi = (size_t)row * zld + c_off + h + c;
+        const float gz = g_zout[zi];
+        if (which) {
+          gp = gz;  // g_b
+        } else {
+          const float x = params[(size_t)row * zld + 2 * c];
+          const float gl = g_log_s ? g_log_s[(size_t)row * (zld / 2) + c] : 0.f;
+          const float z1 = zmid[zi];
+          float s, ds;
+          if (scaling == 0) { const float t = tanhf(x); s = (t + 1.f) + 1e-6f; ds = 1.f - t * t; }
+          else if (scaling == 1) { s = expf(x); ds = s; }
+          else if (scaling == 2) { const float sg = 1.f / (1.f + expf(-(x + 10.f))); s = sg + 1e-6f; ds = sg * (1.f - sg); }
+          else { s = 1.f; ds = 0.f; }
+          // log_s = log(s) for tanh/sigmoid, = x for exp (d log_s / dx = 1), = 0 for translate
+          const float dls = (scaling == 1) ? 1.f : (scaling == 3 ? 0.f : ds / s);
+          gp = gz * z1 * ds + gl * dls;
+          g_zmid[zi] = s * gz;
+        }
+      }
+      put_act(g_params + (size_t)row * kpad + j, gp);
+    }
+  }
+}
+
+// de-interleave the `end` weight gradient: tmp[2c + p][k] -> out[p * h + c][k]; tmp[..][n_ch] holds the bias grad
+__global__ void end_grad_unpack_kernel(const float* __restrict__ tmp, int ldt, int h, int n_ch, float* __restrict__ gw,
+                                       float* __restrict__ gb) {
+  const int total = 2 * h * (n_ch + 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % (n_ch + 1), r = i / (n_ch + 1);
+    const int c = r >> 1, p = r & 1;
+    const float v = tmp[(size_t)r * ldt + k];
+    if (k < n_ch) gw[(size_t)(p * h + c) * n_ch + k] = v;
+    else gb[p * h + c] = v;
+  }
+}
+
+template <typename T>
+static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const PlanView& pv,
+                         const radtts_flow_buffers& f, const radtts_flow_grad_buffers& g, int accumulate_ctx,
+                         cudaStream_t st) {
+  const int prec = sizeof(T) == 4 ? RADTTS_PREC_FP32 : RADTTS_PREC_BF16;
+  FlowLayout L = flow_layout(d, prec, 1);
+  const int h = d.c_active / 2, nc = d.n_ch, k = d.ksize, nl = d.n_layers;
+  const int rows = pv.rows_alloc;
+  RowMeta meta{pv.pos(), pv.rem()};
+  const T* x = reinterpret_cast<const T*>(f.x);
+  const T* r = reinterpret_cast<const T*>(f.r);
+  T* gu = reinterpret_cast<T*>(g.g_u);
+  T* gv = reinterpret_cast<T*>(g.g_v);
+  T* gx0 = reinterpret_cast<T*>(g.g_x0);
+  T* gparams = reinterpret_cast<T*>(g.g_params);
+
+  // 1. coupling backward
+  coupling_bwd_kernel<T><<<grid_for((size_t)rows * L.end_kpad), 256, 0, st>>>(
+      g.g_zout, g.g_log_s, f.params, f.zmid, meta, pv.hdr(), d.z_ld, d.c_off, h, d.scaling, L.end_kpad, g.g_zmid, gparams);
+  RB_TRY(after_launch());
+
+  GemmDesc gd{};
+  gd.rows_alloc = rows;
+  gd.plan = pv.hdr();
+  // 2. end dgrad
+  gd.nseg = 1;
+  gd.seg[0] = Seg{gparams, L.end_kpad, 0, 0, L.end_kpad};
+  gd.w = base + L.w_end_t; gd.ldw = L.end_kpad; gd.N = nc;
+  {
+    EpiEndDgrad<T> e{r, nl * nc, gu, nl, nc, rows, meta};
+    RB_TRY((run_gemm<T>(gd, e, st)));
+  }
+  // 3. layers, last to first
+  for (int i = nl - 1; i >= 0; --i) {
+    gd.nseg = 1;
+    gd.seg[0] = Seg{gu + (size_t)i * rows * nc, nc, 0, 0, nc};
+    if (i + 1 < nl) {
+      for (int t = 0; t < k; ++t)
+        gd.seg[1 + t] = Seg{gv + (size_t)(i + 1) * rows * nc, nc, -((t - k / 2) << (i + 1)), 0, nc};
+      gd.nseg = 1 + k;
+    }
+    gd.w = base + L.w_dg[i]; gd.ldw = L.dg_k[i]; gd.N = nc;
+    EpiDgradAct<T> e{x + (size_t)(i + 1) * rows * nc, nc, gv + (size_t)i * rows * nc, nc, meta, ACT_SOFTPLUS,
+                     d.partial_padding, i, k};
+    RB_TRY((run_gemm<T>(gd, e, st)));
+  }
+  // 4. g_x0 and start dgrad
+  gd.nseg = k;
+  for (int t = 0; t < k; ++t) gd.seg[t] = Seg{gv, nc, -(t - k / 2), 0, nc};
+  gd.w = base + L.w_dg0; gd.ldw = k * nc; gd.N = nc;
+  {
+    EpiDgradAct<T> e{nullptr, nc, gx0, nc, meta, ACT_NONE, 0, 0, k};
+    RB_TRY((run_gemm<T>(gd, e, st)));
+  }
+  gd.nseg = 1;
+  gd.seg[0] = Seg{gx0, nc, 0, 0, nc};
+  gd.w = base + L.w_start_t; gd.ldw = nc; gd.N = L.ctx_ld + 128;
+  {
+    EpiStartDgrad e{g.g_ctx, d.n_ctx, L.ctx_ld, g.g_zmid, d.c_off, h, d.z_ld, accumulate_ctx, meta};
+    RB_TRY((run_gemm<T>(gd, e, st)));
+  }
+  // 5. 1x1 conv dgrad (fp32 always)
+  gd.nseg = 1;
+  gd.seg[0] = Seg{g.g_zmid, d.z_ld, 0, 0, d.z_ld};
+  gd.w = base + L.w_inv_t; gd.ldw = d.z_ld; gd.N = d.z_ld;
+  {
+    EpiStoreF32 e{g.g_zin, d.z_ld, meta, 1};
+    RB_TRY(launch_rowgemm_simt(gd, e, st));
+  }
+
+  // 6. weight gradients -------------------------------------------------------------------------------
+  // bf16: every problem of this flow goes into ONE batched tcgen05 launch; fp32: SIMT launches with atomics.
+  WgradBatch batch;
+  batch.rows_alloc = rows;
+  auto wgrad = [&](const WgradProb& p, bool accumulate) -> int {
+    if constexpr (sizeof(T) == 2) {
+      if (batch.add(p, accumulate)) return 0;
+    }
+    return launch_wgrad_simt<T, T>(p, pv.hdr(), rows, st);
+  };
+  // 1x1 conv: dW_full[c][j] = sum_r g_zmid[r][c] zin[r][j]   (fp32 always)
+  {
+    RB_CUDA(cudaMemsetAsync(g.g_w_inv_full, 0, (size_t)d.z_ld * d.z_ld * sizeof(float), st));
+    WgradProb p{g.g_zmid, d.z_ld, 0, d.z_ld, f.zin, d.z_ld, 0, d.z_ld, 0, g.g_w_inv_full, d.z_ld, 1};
+    RB_TRY((launch_wgrad_simt<float, float>(p, pv.hdr(), rows, st)));
+  }
+  // end: interleaved rows into scratch, the n_layers K-blocks of r accumulate; bias = column sums of g_params
+  float* tmp = g.scratch_f32;
+  const int ldt = nc + 1;
+  RB_CUDA(cudaMemsetAsync(tmp, 0, (size_t)d.z_ld * ldt * sizeof(float), st));
+  for (int l = 0; l < nl; ++l) {
+    WgradProb p{gparams, L.end_kpad, 0, d.z_ld, r, nl * nc, l * nc, nc, 0, tmp, ldt, 1};
+    RB_TRY(wgrad(p, true));
+  }
+  RB_TRY((launch_colsum<T>(gparams, L.end_kpad, 0, d.z_ld, meta, 0, 0, k, pv.hdr(), rows, tmp + nc, ldt, false, st)));
+  for (int i = 0; i < nl; ++i) {
+    const T* gui = gu + (size_t)i * rows * nc;
+    const T* gvi = gv + (size_t)i * rows * nc;
+    // res_skip_i: dW[n][c] = sum_r g_u_i[r][n] x_{i+1}[r][c]
+    RB_CUDA(cudaMemsetAsync(g.g_w_rs[i], 0, (size_t)nc * nc * sizeof(float), st));
+    {
+      WgradProb p{gui, nc, 0, nc, x + (size_t)(i + 1) * rows * nc, nc, 0, nc, 0, g.g_w_rs[i], nc, 1};
+      RB_TRY(wgrad(p, false));
+    }
+    RB_TRY((launch_colsum<T>(gui, nc, 0, nc, meta, 0, 0, k, pv.hdr(), rows, g.g_b_rs[i], 1, true, st)));
+    // in_layer_i (tap-major output [t][n][c]): dW[t][n][c] = sum_r g_v_i[r][n] x_i[r + (t - half) d][c]
+    RB_CUDA(cudaMemsetAsync(g.g_w_in[i], 0, (size_t)nc * nc * k * sizeof(float), st));
+    for (int t = 0; t < k; ++t) {
+      WgradProb p{gvi, nc, 0, nc, x + (size_t)i * rows * nc, nc, 0, nc, (t - k / 2) << i,
+                  g.g_w_in[i] + (size_t)t * nc * nc, nc, 1};
+      RB_TRY(wgrad(p, false));
+    }
+    // bias sits outside the partial-conv renormalisation: g_bias = sum_r g_v / ratio
+    RB_TRY((launch_colsum<T>(gvi, nc, 0, nc, meta, d.partial_padding, i, k, pv.hdr(), rows, g.g_b_in[i], 1, true, st)));
+  }
+  // start: the two K segments land directly in the reference layout [z0 (h) | ctx (n_ctx)]
+  {
+    const int ldo = h + d.n_ctx;
+    RB_CUDA(cudaMemsetAsync(g.g_w_start, 0, (size_t)nc * ldo * sizeof(float), st));
+    WgradProb pc{gx0, nc, 0, nc, f.ctx, L.ctx_ld, 0, d.n_ctx, 0, g.g_w_start + h, ldo, 1};
+    RB_TRY(wgrad(pc, false));
+    WgradProb pz{gx0, nc, 0, nc, f.z0, 128, 0, h, 0, g.g_w_start, ldo, 1};
+    RB_TRY(wgrad(pz, false));
+    RB_TRY((launch_colsum<T>(gx0, nc, 0, nc, meta, 0, 0, k, pv.hdr(), rows, g.g_b_start, 1, true, st)));
+  }
+  RB_TRY(batch.launch(pv.hdr(), st));
+  end_grad_unpack_kernel<<<grid_for((size_t)2 * h * ldt), 256, 0, st>>>(tmp, ldt, h, nc, g.g_w_end, g.g_b_end);
+  RB_TRY(after_launch());
+  return 0;
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" int radtts_flowstep_backward(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
+                                        int Tmax, const radtts_flow_buffers* fwd, const radtts_flow_grad_buffers* g,
+                                        int accumulate_ctx, int precision, void* stream) {
+  RB_TRY(check_dims(dims));
+  if (!prepared || !plan || !fwd || !g || B <= 0 || Tmax <= 0) return RADTTS_ERR_INVALID_ARG;
+  if (!fwd->ctx || !fwd->zin || !fwd->zmid || !fwd->z0 || !fwd->x || !fwd->r || !fwd->params) return RADTTS_ERR_INVALID_ARG;
+  if (!g->g_zout || !g->g_zin || !g->g_ctx || !g->g_zmid || !g->g_params || !g->g_u || !g->g_v || !g->g_x0 ||
+      !g->g_w_inv_full || !g->g_w_start || !g->g_b_start || !g->g_w_end || !g->g_b_end || !g->scratch_f32)
+    return RADTTS_ERR_INVALID_ARG;
+  for (int i = 0; i < dims->n_layers; ++i)
+    if (!g->g_w_in[i] || !g->g_b_in[i] || !g->g_w_rs[i] || !g->g_b_rs[i]) return RADTTS_ERR_INVALID_ARG;
+  PlanView pv = make_plan_view(plan, B, Tmax);
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(prepared);
+  if (precision == RADTTS_PREC_FP32)
+    return backward_impl<float>(*dims, base, pv, *fwd, *g, accumulate_ctx, (cudaStream_t)stream);
+  if (precision == RADTTS_PREC_BF16)
+    return backward_impl<__nv_bfloat16>(*dims, base, pv, *fwd, *g, accumulate_ctx, (cudaStream_t)stream);
+  return RADTTS_ERR_INVALID_ARG;
+}

@@ -283,21 +283,31 @@ struct EpiDgradAct {
   }
 };
 
-// dgrad of `start`: columns [0, n_ctx) -> g_ctx (fp32), columns [ctx_ld, ctx_ld + h) -> g_zmid[:, c_off + c] += acc
+// dgrad of `start`: columns [0, ctx_ld) -> g_ctx (fp32, optionally accumulated over flows),
+// columns [ctx_ld, ctx_ld + h) -> g_zmid[:, c_off + c] += acc   (gradient reaching z0 through the WN)
 struct EpiStartDgrad {
-  float* g_ctx; int ld_ctx; int n_ctx;
-  float* g_zmid; int c_off, h, ctx_ld, zld;
+  float* g_ctx; int n_ctx; int ctx_ld;
+  float* g_zmid; int c_off, h, zld;
+  int accumulate;
   RowMeta meta;
   template <int W>
   __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W]) const {
     const bool ok = meta.valid(row);
+    if (col0 + W <= ctx_ld) {
+      float y[W];
+      float* dst = g_ctx + (size_t)row * ctx_ld + col0;
+      if (accumulate) Act<float>::ldv<W>(dst, y);
 #pragma unroll
-    for (int i = 0; i < W; ++i) {
-      const int c = col0 + i;
-      if (c < ctx_ld) {
-        if (c < ld_ctx) g_ctx[(size_t)row * ld_ctx + c] = (ok && c < n_ctx) ? acc[i] : 0.f;
-      } else if (c < ctx_ld + h) {
-        if (ok) g_zmid[(size_t)row * zld + c_off + (c - ctx_ld)] += acc[i];
+      for (int i = 0; i < W; ++i) {
+        const float v = (ok && col0 + i < n_ctx) ? acc[i] : 0.f;
+        y[i] = accumulate ? y[i] + v : v;
+      }
+      Act<float>::stv<W>(dst, y);
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        const int c = col0 + i - ctx_ld;
+        if (ok && c >= 0 && c < h) g_zmid[(size_t)row * zld + c_off + c] += acc[i];
       }
     }
   }
@@ -401,7 +411,7 @@ __global__ void __launch_bounds__(kSimtThreads) rowgemm_simt(GemmDesc d, Epi epi
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = row0 + ty * 8 + i;
-      if (row < rows_used) epi.template operator()<8>(row, col0, acc[i]);
+      epi.template operator()<8>(row, col0, acc[i]);  // rows past the packed range are gap rows (zeros)
     }
   }
 }

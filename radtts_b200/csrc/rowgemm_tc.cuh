@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
         uint32_t r[16];
         tmem_ld16(t_addr + c, r);
         tmem_ld_wait();
-        if (row < rows_used && n0 + c < p.N) {
+        if (n0 + c < p.N) {  // rows past the packed range are gap rows: functors write zeros there
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
@@ -238,8 +238,7 @@ inline int launch_rowgemm_tc(const GemmDesc& d, const Epi& epi, cudaStream_t str
   p.plan = d.plan;
   if (d.N % 16) return RADTTS_ERR_INVALID_ARG;
   p.bn = d.N <= kTcMaxBN ? d.N : kTcMaxBN;
-  if (d.N % p.bn) return RADTTS_ERR_UNSUPPORTED;
-  p.n_tiles_n = d.N / p.bn;
+  p.n_tiles_n = ceil_div(d.N, p.bn);  // a partial last tile reads zero-filled weight rows and is masked on store
   const void* bases[kTcMaxMaps];
   int lds[kTcMaxMaps];
   int nmaps = 0;

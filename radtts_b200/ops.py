@@ -54,6 +54,13 @@ class FlowBuffers(ctypes.Structure):
     _fields_ = [(n, _P) for n in ("ctx", "zin", "zmid", "zout", "z0", "x", "r", "params", "log_s")]
 
 
+class FlowGradBuffers(ctypes.Structure):
+    _fields_ = [(n, _P) for n in ("g_zout", "g_log_s", "g_zin", "g_ctx", "g_zmid", "g_params", "g_u", "g_v", "g_x0",
+                                  "g_w_inv_full", "g_w_start", "g_b_start")] + \
+               [("g_w_in", _P * MAX_LAYERS), ("g_b_in", _P * MAX_LAYERS), ("g_w_rs", _P * MAX_LAYERS),
+                ("g_b_rs", _P * MAX_LAYERS), ("g_w_end", _P), ("g_b_end", _P), ("scratch_f32", _P)]
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
@@ -226,71 +233,151 @@ def prepare_flow(dims, ws, prec, want_backward, device):
     return blob
 
 
-def _alloc_buffers(dims, plan, prec, device, zin, ctx_packed):
+class _Pool:
+    """Zero-initialised scratch tensors, recycled across steps.  The kernels rely on every packed buffer being
+    FINITE beyond the rows they write (stale values are multiplied by zero rows; NaN garbage would not be)."""
+
+    def __init__(self):
+        self.free = {}
+
+    def get(self, shape, dtype, device):
+        key = (tuple(shape), dtype, device.type, device.index)
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop()
+        return torch.zeros(shape, dtype=dtype, device=device)
+
+    def put(self, t):
+        key = (tuple(t.shape), t.dtype, t.device.type, t.device.index)
+        self.free.setdefault(key, []).append(t)
+
+    def clear(self):
+        self.free.clear()
+
+
+POOL = _Pool()
+
+
+class _Lease:
+    """A set of pooled tensors that goes back to the pool when released or garbage collected."""
+
+    def __init__(self):
+        self.t = {}
+
+    def take(self, name, shape, dtype, device):
+        self.t[name] = POOL.get(shape, dtype, device)
+        return self.t[name]
+
+    def release(self):
+        for v in self.t.values():
+            POOL.put(v)
+        self.t = {}
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def _fwd_buffers(dims, plan, prec, device, zin, ctx_packed, lease, keep_params):
     act = _act_dtype(prec)
     rows = plan.rows
+    zout = torch.zeros((rows, dims.z_ld), dtype=torch.float32, device=device)
+    log_s = torch.zeros((rows, dims.z_ld // 2), dtype=torch.float32, device=device)
     b = {
-        "zmid": torch.empty((rows, dims.z_ld), dtype=torch.float32, device=device),
-        "zout": torch.zeros((rows, dims.z_ld), dtype=torch.float32, device=device),
-        "z0": torch.empty((rows, 128), dtype=act, device=device),
-        "x": torch.empty((dims.n_layers + 1, rows, dims.n_ch), dtype=act, device=device),
-        "r": torch.empty((rows, dims.n_layers * dims.n_ch), dtype=act, device=device),
-        "params": torch.empty((rows, dims.z_ld), dtype=torch.float32, device=device),
-        "log_s": torch.zeros((rows, dims.z_ld // 2), dtype=torch.float32, device=device),
+        "zin": zin, "ctx": ctx_packed, "zout": zout, "log_s": log_s,
+        "zmid": lease.take("zmid", (rows, dims.z_ld), torch.float32, device),
+        "z0": lease.take("z0", (rows, 128), act, device),
+        "x": lease.take("x", (dims.n_layers + 1, rows, dims.n_ch), act, device),
+        "r": lease.take("r", (rows, dims.n_layers * dims.n_ch), act, device),
+        "params": lease.take("params", (rows, dims.z_ld), torch.float32, device) if keep_params else None,
     }
-    s = FlowBuffers(ctx=_p(ctx_packed), zin=_p(zin), zmid=_p(b["zmid"]), zout=_p(b["zout"]), z0=_p(b["z0"]),
-                    x=_p(b["x"]), r=_p(b["r"]), params=_p(b["params"]), log_s=_p(b["log_s"]))
+    s = FlowBuffers(ctx=_p(ctx_packed), zin=_p(zin), zmid=_p(b["zmid"]), zout=_p(zout), z0=_p(b["z0"]),
+                    x=_p(b["x"]), r=_p(b["r"]), params=_p(b["params"]), log_s=_p(log_s))
     return b, s
 
 
-def run_flowstep(dims, blob, plan, zin, ctx_packed, prec, inverse):
-    """zin fp32 [rows][z_ld], ctx_packed act [rows][ctx_ld].  Returns (zout, log_s or None, buffers)."""
+def run_flowstep(dims, blob, plan, zin, ctx_packed, prec, inverse, lease, keep_params=False):
+    """zin fp32 [rows][z_ld], ctx_packed act [rows][ctx_ld].  Returns (zout, log_s or None, buffers, struct)."""
     dev = zin.device
-    bufs, s = _alloc_buffers(dims, plan, prec, dev, zin, ctx_packed)
+    bufs, s = _fwd_buffers(dims, plan, prec, dev, zin, ctx_packed, lease, keep_params)
     L = _lib.lib()
     fn = L.radtts_flowstep_inverse if inverse else L.radtts_flowstep_forward
     _lib.check(fn(ctypes.byref(dims), _lib.ptr(blob), plan.ptr, plan.B, plan.Tmax, ctypes.byref(s), prec,
                   ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
                "radtts_flowstep_inverse" if inverse else "radtts_flowstep_forward")
-    return bufs["zout"], (None if inverse else bufs["log_s"]), bufs
+    return bufs["zout"], (None if inverse else bufs["log_s"]), bufs, s
 
 
-class _FlowStepFn(torch.autograd.Function):
-    """One decoder flow on packed rows.  inputs: zin [rows][z_ld] fp32, ctx [rows][ctx_ld] act, then the
-    effective weights (so that weight-norm / LUS parameter gradients are left to autograd)."""
+class _FlowStackFn(torch.autograd.Function):
+    """A run of consecutive decoder flows on packed rows (the whole 8-flow stack in RADTTS.forward, a single flow
+    for FlowStep.forward).  Inputs: zin [rows][z_ld] fp32, ctx [rows][ctx_ld] act, then the effective weights of
+    every flow (weight-norm / LUS parameter gradients are left to autograd).  Returns (zout, log_s_0, ...)."""
 
     @staticmethod
-    def forward(ctx, zin, ctx_packed, plan, dims, prec, inverse, *ws):
-        need_bwd = (not inverse) and any(t.requires_grad for t in (zin, ctx_packed) + tuple(ws))
-        blob = prepare_flow(dims, ws, prec, need_bwd, zin.device)
-        zout, log_s, bufs = run_flowstep(dims, blob, plan, zin.contiguous(), ctx_packed, prec, inverse)
-        if need_bwd:
-            ctx.saved = (zin, ctx_packed, plan, dims, prec, blob, bufs, [w.shape for w in ws])
+    def forward(ctx, zin, ctx_packed, plan, dims_list, prec, inverse, n_per_flow, *ws):
+        need_bwd = (not inverse) and any(ctx.needs_input_grad)
+        order = range(len(dims_list))
         if inverse:
-            return zout
-        return zout, log_s
+            order = reversed(order)
+        z = zin.contiguous()
+        log_s_all = [None] * len(dims_list)
+        saved = [None] * len(dims_list)
+        for i in order:
+            dims = dims_list[i]
+            w_i = ws[i * n_per_flow:(i + 1) * n_per_flow]
+            blob = prepare_flow(dims, w_i, prec, need_bwd, z.device)
+            lease = _Lease()
+            zout, log_s, bufs, _ = run_flowstep(dims, blob, plan, z, ctx_packed, prec, inverse, lease, need_bwd)
+            if need_bwd:
+                saved[i] = (blob, bufs, lease)
+            else:
+                lease.release()
+            log_s_all[i] = log_s
+            z = zout
+        if need_bwd:
+            ctx.saved = (plan, dims_list, prec, n_per_flow, saved, [tuple(w.shape) for w in ws], ctx_packed.dtype)
+        if inverse:
+            return z
+        return (z,) + tuple(log_s_all)
 
     @staticmethod
-    def backward(ctx, g_zout, g_log_s=None):
+    def backward(ctx, g_zout, *g_log_s):
         from . import ops_backward
-        return ops_backward.flowstep_backward(ctx.saved, g_zout, g_log_s)
+        return ops_backward.flow_stack_backward(ctx.saved, g_zout, g_log_s)
 
 
 def ctx_ld_of(n_ctx):
     return (n_ctx + 63) // 64 * 64
 
 
-def flow_step_packed(flow, zin, ctx_packed, plan, z_ld, c_active, inverse=False, prec=None):
+def flow_stack_packed(flows, zin, ctx_packed, plan, z_ld, actives, inverse=False, prec=None):
+    """Runs `flows` (in order; reversed when inverse) on packed rows.  actives[i] = channels flow i transforms."""
     prec = current_precision() if prec is None else prec
-    dims = _flow_dims(flow, z_ld, c_active)
-    ws = _flow_weight_list(flow, inverse)
-    out = _FlowStepFn.apply(zin, ctx_packed, plan, dims, prec, inverse, *ws)
+    dims_list = [_flow_dims(f, z_ld, c) for f, c in zip(flows, actives)]
+    ws = []
+    for f in flows:
+        w = _flow_weight_list(f, inverse)
+        ws += w
+    n_per = len(ws) // len(flows)
+    out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, n_per, *ws)
     if inverse:
         return out
-    zout, log_s = out
-    inv = flow.invtbl_conv
-    log_det = inv.log_det() if hasattr(inv, "log_det") else torch.logdet(inv.conv.weight.squeeze(-1)).clone()
-    return zout, log_det, log_s
+    zout, log_s = out[0], list(out[1:])
+    log_dets = []
+    for f in flows:
+        inv = f.invtbl_conv
+        log_dets.append(inv.log_det() if hasattr(inv, "log_det")
+                        else torch.logdet(inv.conv.weight.squeeze(-1)).clone())
+    return zout, log_dets, log_s
+
+
+def flow_step_packed(flow, zin, ctx_packed, plan, z_ld, c_active, inverse=False, prec=None):
+    out = flow_stack_packed([flow], zin, ctx_packed, plan, z_ld, [c_active], inverse, prec)
+    if inverse:
+        return out
+    return out[0], out[1][0], out[2][0]
 
 
 def _is_fused_flow(flow):
@@ -319,6 +406,15 @@ def flow_step(flow, z, context, inverse=False, seq_lens=None):
     return unpack(zout, plan, C, 1, z_ld - C), log_det, unpack(log_s, plan, C // 2, 1, 0)
 
 
+def _active_channels(model, z_ld):
+    actives, c = [], z_ld
+    for i in range(len(model.flows)):
+        if i in model.exit_steps:
+            c -= model.n_early_size
+        actives.append(c)
+    return actives
+
+
 def decoder_forward(model, mel, context, out_lens):
     """Training direction of the decoder loop (reference radtts.py:414,431-444) on packed frames: one pack,
     n_flows fused flow steps operating in place on the column suffix that is still active, one unpack."""
@@ -330,14 +426,9 @@ def decoder_forward(model, mel, context, out_lens):
     z = pack(mel, plan, g, torch.float32, z_ld, 0, z_ld)
     n_ctx = context.shape[1]
     ctxp = pack(context, plan, 1, _act_dtype(prec), ctx_ld_of(n_ctx), 0, ctx_ld_of(n_ctx))
-    log_s_list, log_det_list = [], []
-    c_active = z_ld
-    for i, flow in enumerate(model.flows):
-        if i in model.exit_steps:
-            c_active -= model.n_early_size
-        z, log_det, log_s = flow_step_packed(flow, z, ctxp, plan, z_ld, c_active, False, prec)
-        log_det_list.append(log_det)
-        log_s_list.append(unpack(log_s, plan, c_active // 2, 1, 0))
+    actives = _active_channels(model, z_ld)
+    z, log_det_list, log_s = flow_stack_packed(list(model.flows), z, ctxp, plan, z_ld, actives, False, prec)
+    log_s_list = [unpack(ls, plan, c // 2, 1, 0) for ls, c in zip(log_s, actives)]
     return unpack(z, plan, z_ld, 1, 0), log_det_list, log_s_list
 
 
@@ -351,14 +442,7 @@ def decoder_inverse(model, residual, context, out_lens):
     z = pack(residual, plan, 1, torch.float32, z_ld, 0, z_ld)
     n_ctx = context.shape[1]
     ctxp = pack(context, plan, 1, _act_dtype(prec), ctx_ld_of(n_ctx), 0, ctx_ld_of(n_ctx))
-    actives = []
-    c_active = z_ld
-    for i in range(len(model.flows)):
-        if i in model.exit_steps:
-            c_active -= model.n_early_size
-        actives.append(c_active)
-    for i in reversed(range(len(model.flows))):
-        z = flow_step_packed(model.flows[i], z, ctxp, plan, z_ld, actives[i], True, prec)
+    z = flow_stack_packed(list(model.flows), z, ctxp, plan, z_ld, _active_channels(model, z_ld), True, prec)
     return unpack(z, plan, z_ld // g, g, 0)
 
 

@@ -1,0 +1,77 @@
+"""Backward orchestration of the decoder flow stack (host plumbing for radtts_flowstep_backward)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import ops
+
+
+def flow_stack_backward(saved, g_zout, g_log_s):
+    plan, dims_list, prec, n_per, saved_list, w_shapes, ctx_dtype = saved
+    dev = plan.buf.device
+    rows = plan.rows
+    act = ops._act_dtype(prec)
+    L = _lib.lib()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    z_ld = dims_list[0].z_ld
+    ctx_ld = ops.ctx_ld_of(dims_list[0].n_ctx)
+    g_z = torch.zeros((rows, z_ld), dtype=torch.float32, device=dev) if g_zout is None else g_zout.float().contiguous()
+    g_ctx = torch.zeros((rows, ctx_ld), dtype=torch.float32, device=dev)
+    grads = [None] * len(w_shapes)
+    first = True
+    for i in reversed(range(len(dims_list))):
+        dims = dims_list[i]
+        blob, bufs, lease = saved_list[i]
+        nl, nc, k = dims.n_layers, dims.n_ch, dims.ksize
+        h = dims.c_active // 2
+        gl = g_log_s[i] if i < len(g_log_s) else None
+        gl = None if gl is None else gl.float().contiguous()
+        scratch = ops._Lease()
+        kpad = (z_ld + 63) // 64 * 64
+        g_zin = torch.zeros((rows, z_ld), dtype=torch.float32, device=dev)
+        fwd = ops.FlowBuffers(ctx=ops._p(bufs["ctx"]), zin=ops._p(bufs["zin"]), zmid=ops._p(bufs["zmid"]),
+                              zout=ops._p(bufs["zout"]), z0=ops._p(bufs["z0"]), x=ops._p(bufs["x"]), r=ops._p(bufs["r"]),
+                              params=ops._p(bufs["params"]), log_s=ops._p(bufs["log_s"]))
+        gw_inv_full = torch.empty((z_ld, z_ld), dtype=torch.float32, device=dev)
+        gw_start = torch.empty((nc, h + dims.n_ctx), dtype=torch.float32, device=dev)
+        gb_start = torch.empty(nc, dtype=torch.float32, device=dev)
+        gw_in = [torch.empty((k, nc, nc), dtype=torch.float32, device=dev) for _ in range(nl)]
+        gb_in = [torch.empty(nc, dtype=torch.float32, device=dev) for _ in range(nl)]
+        gw_rs = [torch.empty((nc, nc), dtype=torch.float32, device=dev) for _ in range(nl)]
+        gb_rs = [torch.empty(nc, dtype=torch.float32, device=dev) for _ in range(nl)]
+        gw_end = torch.empty((2 * h, nc), dtype=torch.float32, device=dev)
+        gb_end = torch.empty(2 * h, dtype=torch.float32, device=dev)
+        g = ops.FlowGradBuffers(
+            g_zout=ops._p(g_z), g_log_s=ops._p(gl), g_zin=ops._p(g_zin), g_ctx=ops._p(g_ctx),
+            g_zmid=ops._p(scratch.take("g_zmid", (rows, z_ld), torch.float32, dev)),
+            g_params=ops._p(scratch.take("g_params", (rows, kpad), act, dev)),
+            g_u=ops._p(scratch.take("g_u", (nl, rows, nc), act, dev)),
+            g_v=ops._p(scratch.take("g_v", (nl, rows, nc), act, dev)),
+            g_x0=ops._p(scratch.take("g_x0", (rows, nc), act, dev)),
+            g_w_inv_full=ops._p(gw_inv_full), g_w_start=ops._p(gw_start), g_b_start=ops._p(gb_start),
+            g_w_end=ops._p(gw_end), g_b_end=ops._p(gb_end),
+            scratch_f32=ops._p(scratch.take("scratch_f32", (z_ld, nc + 1), torch.float32, dev)))
+        for j in range(nl):
+            g.g_w_in[j], g.g_b_in[j] = ops._p(gw_in[j]), ops._p(gb_in[j])
+            g.g_w_rs[j], g.g_b_rs[j] = ops._p(gw_rs[j]), ops._p(gb_rs[j])
+        _lib.check(L.radtts_flowstep_backward(ctypes.byref(dims), _lib.ptr(blob), plan.ptr, plan.B, plan.Tmax,
+                                              ctypes.byref(fwd), ctypes.byref(g), 0 if first else 1, prec, stream),
+                   "radtts_flowstep_backward")
+        first = False
+        scratch.release()
+        lease.release()
+        saved_list[i] = None
+        base = i * n_per
+        out = [gw_inv_full[dims.c_off:, dims.c_off:], gw_start, gb_start]
+        for j in range(nl):
+            out += [gw_in[j].permute(1, 2, 0), gb_in[j]]
+        for j in range(nl):
+            out += [gw_rs[j], gb_rs[j]]
+        out += [gw_end, gb_end]
+        for j, t in enumerate(out):
+            assert tuple(t.shape) == tuple(w_shapes[base + j]), (j, t.shape, w_shapes[base + j])
+            grads[base + j] = t
+        g_z = g_zin
+    g_ctx_out = g_ctx if ctx_dtype == torch.float32 else g_ctx.to(ctx_dtype)
+    return (g_z, g_ctx_out, None, None, None, None, None) + tuple(grads)

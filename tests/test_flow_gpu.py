@@ -99,3 +99,49 @@ def test_flowstep_module_api_and_roundtrip(model):
         assert _close(_valid(back, lens), _valid(z, lens), 0, 1e-4)
     finally:
         ops.set_precision(None)
+
+
+@pytest.mark.parametrize("prec,rtol_in,rtol_w", [("fp32", 2e-3, 3e-3), ("bf16", 0.08, 0.05)])
+def test_decoder_gradients_vs_reference_golden(model, gold, prec, rtol_in, rtol_w):
+    """Backward of the 8-flow stack (dgrad + wgrad + coupling + LUS) against the gradients PyTorch autograd
+    produced for the unmodified reference (golden g_mel, g_context, per-parameter norms and samples)."""
+    ops.set_precision(prec)
+    try:
+        model.zero_grad(set_to_none=True)
+        batch = synth.synth_batch(3, 70, 24, seed=1234)
+        mel = batch["mel"].cuda().requires_grad_(True)
+        ctx = torch.from_numpy(gold["context"]).cuda().requires_grad_(True)
+        out_lens = batch["out_lens"].cuda()
+        z, logdets, log_s = ops.decoder_forward(model, mel, ctx, out_lens)
+        loss, _ = oflow.flow_loss(z, logdets, log_s, out_lens)
+        loss.backward()
+        tol = 1e-3 if prec == "fp32" else 3e-3
+        assert abs(float(loss) - float(gold["dec_loss"])) < tol * abs(float(gold["dec_loss"]))
+
+        def rel(a, b):
+            a, b = a.double().cpu().flatten(), torch.as_tensor(b).double().flatten()
+            return float((a - b).norm() / (b.norm() + 1e-30))
+
+        r_mel, r_ctx = rel(mel.grad, gold["g_mel"]), rel(ctx.grad, gold["g_context"])
+        print("rel err g_mel %.2e g_context %.2e" % (r_mel, r_ctx))
+        assert r_mel < rtol_in and r_ctx < rtol_in
+        params = dict(model.named_parameters())
+        worst = 0.0
+        for name, sums, sample in zip(gold["grad_names"], gold["grad_sums"], gold["grad_samples"]):
+            name = str(name)
+            g = params[name].grad
+            assert g is not None, name
+            if name.endswith(("invtbl_conv.lower", "invtbl_conv.upper")):
+                # the reference masks these with tril/triu inside forward; so do we
+                pass
+            err = abs(float(g.double().norm()) - sums[1]) / (sums[1] + 1e-12)
+            got = g.detach().flatten()[::1009][:64].float().cpu().numpy()
+            want = sample[:len(got)]
+            serr = np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-12)
+            worst = max(worst, err, serr if np.linalg.norm(want) > 1e-8 else 0.0)
+            assert err < rtol_w, (name, err)
+            if np.linalg.norm(want) > 1e-8:
+                assert serr < 4 * rtol_w, (name, serr)
+        print("worst relative parameter-gradient error %.2e" % worst)
+    finally:
+        ops.set_precision(None)
