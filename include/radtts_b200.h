@@ -182,6 +182,23 @@ RADTTS_API int radtts_flowstep_backward(const radtts_flow_dims* dims, const void
                                         int Tmax, const radtts_flow_buffers* fwd, const radtts_flow_grad_buffers* g,
                                         int accumulate_ctx, int precision, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Kernel 3 -- ConvAttention core: pairwise L2 distance + log-softmax over text + log prior + masked softmax.
+ * Replaces: ConvAttention.forward after the key/query projections (reference common.py:907-923) and its
+ * autograd backward.  The (B, C, T1, T2) broadcast temporary of the reference is never materialised.
+ *   q_enc (B, C, T1), k_enc (B, C, T2): projected queries / keys, float32, C <= 128 (80), T2 <= 576.
+ *   prior (B, T1, T2) or NULL; key_lens (B) int64 or NULL (keys >= key_lens[b] are masked in the softmax,
+ *   but -- like the reference -- still take part in the log-softmax).
+ *   attn, attn_logprob (B,1,T1,T2) out; lse (B,T1) out: log-sum-exp of the distances, saved for backward.
+ * backward: g_attn / g_logprob (either may be NULL) -> g_q (may be NULL), g_k; gd_ws is a (B,T1,T2) scratch.
+ * ---------------------------------------------------------------------------------------------- */
+RADTTS_API int radtts_convattn_forward(const float* q_enc, const float* k_enc, const float* prior,
+                                       const int64_t* key_lens, int B, int C, int T1, int T2, float temp, float* attn,
+                                       float* attn_logprob, float* lse, void* stream);
+RADTTS_API int radtts_convattn_backward(const float* q_enc, const float* k_enc, const float* lse, const float* attn,
+                                        const float* g_attn, const float* g_logprob, int has_prior, int B, int C, int T1,
+                                        int T2, float temp, float* gd_ws, float* g_q, float* g_k, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

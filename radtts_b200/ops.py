@@ -469,5 +469,55 @@ def spline_coupling(layer, z, context, inverse, seq_lens):
     raise NotImplementedError
 
 
+class _ConvAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_enc, k_enc, prior, key_lens, temp):
+        q_enc, k_enc = q_enc.float().contiguous(), k_enc.float().contiguous()
+        B, C, T1 = q_enc.shape
+        T2 = k_enc.shape[2]
+        dev = q_enc.device
+        attn = torch.empty((B, 1, T1, T2), dtype=torch.float32, device=dev)
+        logprob = torch.empty_like(attn)
+        lse = torch.empty((B, T1), dtype=torch.float32, device=dev)
+        prior_c = None if prior is None else prior.float().contiguous()
+        lens = None if key_lens is None else key_lens.to(device=dev, dtype=torch.int64).contiguous()
+        L = _lib.lib()
+        _lib.check(L.radtts_convattn_forward(_lib.ptr(q_enc), _lib.ptr(k_enc), _lib.ptr(prior_c), _lib.ptr(lens), B, C,
+                                             T1, T2, ctypes.c_float(temp), _lib.ptr(attn), _lib.ptr(logprob),
+                                             _lib.ptr(lse), _lib.stream_of(q_enc)), "radtts_convattn_forward")
+        ctx.save_for_backward(q_enc, k_enc, lse, attn)
+        ctx.has_prior = prior is not None
+        ctx.temp = temp
+        return attn, logprob
+
+    @staticmethod
+    def backward(ctx, g_attn, g_logprob):
+        q_enc, k_enc, lse, attn = ctx.saved_tensors
+        B, C, T1 = q_enc.shape
+        T2 = k_enc.shape[2]
+        g_attn = None if g_attn is None else g_attn.float().contiguous()
+        g_logprob = None if g_logprob is None else g_logprob.float().contiguous()
+        gd = torch.empty((B, T1, T2), dtype=torch.float32, device=q_enc.device)
+        g_q = torch.empty_like(q_enc)
+        g_k = torch.empty_like(k_enc)
+        L = _lib.lib()
+        _lib.check(L.radtts_convattn_backward(_lib.ptr(q_enc), _lib.ptr(k_enc), _lib.ptr(lse), _lib.ptr(attn),
+                                              _lib.ptr(g_attn), _lib.ptr(g_logprob), int(ctx.has_prior), B, C, T1, T2,
+                                              ctypes.c_float(ctx.temp), _lib.ptr(gd), _lib.ptr(g_q), _lib.ptr(g_k),
+                                              _lib.stream_of(q_enc)), "radtts_convattn_backward")
+        return g_q, g_k, None, None, None
+
+
 def conv_attention(att, queries, keys, mask, key_lens, attn_prior):
-    raise NotImplementedError
+    """ConvAttention.forward (reference common.py:886-924).  The key/query projections are five small convs
+    (< 0.5 % of the step's FLOPs) run through cuDNN; everything after them -- the part that dominates memory
+    traffic in the reference -- is the fused CUDA kernel 3."""
+    _lib.require_cuda(queries, keys)
+    with torch.autocast(device_type="cuda", enabled=False):
+        k_enc = att.key_proj(keys.float())
+        q_enc = att.query_proj(queries.float())
+    if key_lens is None and mask is not None:
+        key_lens = (~mask.squeeze(-1)).sum(1)
+    if mask is None:
+        key_lens = None
+    return _ConvAttnFn.apply(q_enc, k_enc, attn_prior, key_lens, 0.0005)
