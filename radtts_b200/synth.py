@@ -66,6 +66,16 @@ def synth_state_dict(named_shapes, seed=1234):
         if name.endswith("weight_g"):
             v = out[name[:-1] + "v"]
             out[name] = out[name] * v.flatten(1).norm(dim=1).view(out[name].shape)
+        if name.endswith("_orig") and name[:-5] + "_u" in out:
+            # spectral norm divides by sigma = u^T W v: give it (approximate) leading singular vectors, as a trained
+            # checkpoint would hold; random u, v make sigma ~ 0 and drive the LSTMs into chaotic saturation
+            w = out[name].double().flatten(1)
+            u = out[name[:-5] + "_u"].double()
+            for _ in range(30):
+                v = torch.nn.functional.normalize(w.t() @ u, dim=0)
+                u = torch.nn.functional.normalize(w @ v, dim=0)
+            out[name[:-5] + "_u"] = u.float()
+            out[name[:-5] + "_v"] = v.float()
     return out
 
 
