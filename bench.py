@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Headline benchmark: mel frames/s of the RADTTS train step (fwd + bwd + MAS + optimizer) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode train|infer|mas]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Prints ONE JSON line on rank 0 (see the contract in the task statement): whole-job throughput with inputs resident
+in HBM (`value`), the same metric end to end from pinned host buffers (`e2e`), the roofline of the dominant kernel
+(measured live with CUDA events), and the CPU baseline (the oracle port of the reference's hot path) on a bounded
+sample.  `--impl reference` times that CPU oracle alone with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FLOP_PER_FRAME_TRAIN = 635.9e6      # 3 x 211.97 MFLOP per mel frame (fwd + dgrad + wgrad), flow stack only
+FLOP_PER_FRAME_FWD = 211.97e6
+IN_LAYER_FLOP_PER_GROUP = 2 * 5 * 1024 * 1024   # one dilated k5 1024->1024 conv, per frame group (2 mel frames)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def dist_setup(n):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def barrier_sync(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def make_model(device):
+    from radtts_b200 import configs, synth
+    from radtts_b200.radtts import RADTTS
+    torch.manual_seed(1234)
+    model = RADTTS(**configs.model_config("radtts"))
+    synth.load_synth(model, seed=1234)
+    return model.to(device)
+
+
+def pinned_batch(B, T1, T2, seed):
+    from radtts_b200 import synth
+    b = synth.synth_batch(B, T1, T2, seed=seed)
+    return {k: v.pin_memory() for k, v in b.items()}
+
+
+def to_device(hb, device):
+    return {k: v.to(device, non_blocking=True) for k, v in hb.items()}
+
+
+def time_region(fn, steps, world):
+    """CUDA-event timing of `steps` calls bracketed by barrier + synchronize; max over ranks (ms)."""
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier_sync(world)
+    return max_over_ranks(e0.elapsed_time(e1), world)
+
+
+def in_layer_kernel_probe(model, batch, iters=10):
+    """Times the dominant kernel (bf16 tcgen05 row-GEMM of one dilated in_layer conv, K = 5 x 1024) in isolation
+    with CUDA events on the launching stream; returns (ms per launch, frame groups per launch)."""
+    import ctypes
+    from radtts_b200 import _lib, ops
+    dev = batch["mel"].device
+    g = model.n_group_size
+    plan = ops.FramePlan(batch["out_lens"], g, batch["mel"].shape[2] // g)
+    flow = model.flows[0]
+    dims = ops._flow_dims(flow, 160, 160)
+    with torch.no_grad():
+        ws = ops._flow_weight_list(flow, False)
+        blob = ops.prepare_flow(dims, ws, ops.PREC_BF16, False, dev)
+    rows = plan.rows
+    x = torch.randn((dims.n_layers + 1, rows, dims.n_ch), device=dev).to(torch.bfloat16)
+    L = _lib.lib()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def launch():
+        _lib.check(L.radtts_wn_layer_forward(ctypes.byref(dims), _lib.ptr(blob), plan.ptr, plan.B, plan.Tmax,
+                                             _lib.ptr(x), 3, ops.PREC_BF16, stream), "radtts_wn_layer_forward")
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    groups = int((batch["out_lens"] // g).sum())
+    return e0.elapsed_time(e1) / iters, groups
+
+
+def cpu_baseline(B, T1, T2, steps=1, warmup=0):
+    """The oracle port of the reference hot path on the host cores (bounded sample)."""
+    from oracle import train_step as ots
+    from radtts_b200 import configs, synth
+    from radtts_b200.radtts import RADTTS
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    m = RADTTS(**configs.model_config("radtts"))
+    sd = synth.synth_state_dict([(k, v.shape) for k, v in m.state_dict().items()], seed=1234)
+    del m
+    batch = synth.synth_batch(B, T1, T2, seed=99)
+    fps, sec_per_step, frames = ots.time_steps(sd, batch, steps=steps, warmup=warmup, backward=True, threads=threads)
+    return {"value": round(fps, 2), "unit": "mel frames/s", "cores": threads, "kind": "port",
+            "sample": "oracle hot path (ConvAttention + serial MAS + 8 decoder flows fwd+bwd, fp32) on B=%d x %d frames x "
+                      "%d tokens, %d step(s), %.1f s/step" % (B, T1, T2, steps, sec_per_step)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(2, args.t1, args.t2, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    line = {"impl": "reference", "metric": "mel frames/s, RADTTS decoder train step (fwd+bwd+MAS)", "value": cb["value"],
+            "unit": "mel frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+            "data": "synthetic", "config": workload_config(args), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "mel frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "config_ljs_radtts full decoder train step (fwd+bwd+MAS+RAdam), batch %d/GPU x <=%d mel frames "
+                        "x <=%d tokens, 80 mel bins" % (args.batch, args.t1, args.t2),
+            "global_batch": None, "per_gpu_batch": args.batch, "max_frames": args.t1, "max_tokens": args.t2,
+            "parallelism": "dp", "l2": "working set (>1.5 GB of activations per step) exceeds the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--t1", type=int, default=800)
+    ap.add_argument("--t2", type=int, default=150)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: radtts_b200 has no CPU fallback")
+    world, rank, local = dist_setup(args.gpus)
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    from radtts_b200 import _lib, configs
+    from radtts_b200.trainer import TrainStep
+    peaks = load_peaks()
+
+    model = make_model(device).train()
+    ts = TrainStep(model, configs.LOSS_WEIGHTS, bf16=True, ddp=world > 1, device_ids=[local] if world > 1 else None)
+    host_batches = [pinned_batch(args.batch, args.t1, args.t2, seed=1000 + 17 * rank + i) for i in range(2)]
+    dev_batches = [to_device(b, device) for b in host_batches]
+    frames_per_step_local = float(sum(int(b["out_lens"].sum()) for b in host_batches)) / len(host_batches)
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+
+    it = {"i": 0}
+
+    def step_resident():
+        ts.step(dev_batches[it["i"] % len(dev_batches)])
+        it["i"] += 1
+
+    losses = []
+
+    def step_e2e():
+        b = to_device(host_batches[it["i"] % len(host_batches)], device)
+        loss = ts.step(b)
+        losses.append(float(loss.item()))   # device -> host read of the step's result
+        it["i"] += 1
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ms = time_region(step_resident, args.steps, world)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    frames_total = sum_over_ranks(frames_per_step_local, world)
+    value = frames_total * args.steps / (ms / 1e3)
+
+    step_e2e()
+    ms_e2e = time_region(step_e2e, args.steps, world)
+    e2e_value = frames_total * args.steps / (ms_e2e / 1e3)
+
+    roofline = None
+    cb = None
+    if rank == 0:
+        k_ms, groups = in_layer_kernel_probe(model, dev_batches[0])
+        achieved = groups * IN_LAYER_FLOP_PER_GROUP / (k_ms / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "rowgemm_tc_kernel<EpiBiasAct<bf16>> (WN in_layer, dilated k5 1024->1024)",
+                    "achieved": round(achieved, 1), "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                    "frac": round(achieved / peaks["tf_burst"], 4), "traffic": None, "peak_source": peaks["source"] + " burst",
+                    "ms_per_launch": round(k_ms, 4),
+                    "step_frac_of_sustained_peak": round(value / world * FLOP_PER_FRAME_TRAIN / 1e12 / peaks["tf_sustained"], 4)}
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = cpu_baseline(1, args.t1, args.t2, steps=1, warmup=0)
+        except Exception as e:  # the baseline is reported, never required
+            cb = {"value": None, "error": repr(e)}
+    if rank == 0:
+        line = {"metric": "mel frames/s, RADTTS decoder train step (fwd+bwd+MAS)", "value": round(value, 1),
+                "unit": "mel frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
+                "e2e": {"value": round(e2e_value, 1), "unit": "mel frames/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
+                "gpu_launches": int(launches * world), "clocks": clocks, "roofline": roofline, "cpu_baseline": cb,
+                "loss_last": losses[-1] if losses else None}
+        line["config"]["global_batch"] = args.batch * world
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -154,6 +154,12 @@ RADTTS_API int radtts_flowstep_forward(const radtts_flow_dims* dims, const void*
 RADTTS_API int radtts_flowstep_inverse(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
                                        int Tmax, const radtts_flow_buffers* buf, int precision, void* stream);
 
+/* One WN in_layer (ConvNorm + PartialConv1d k5, dilation 2^layer, + softplus; reference common.py:573) in isolation:
+ * x[layer] -> x[layer + 1] inside an act buffer [n_layers + 1][rows][n_ch].  This is the dominant kernel of the
+ * step; the entry point exists so that it can be timed and profiled by itself. */
+RADTTS_API int radtts_wn_layer_forward(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
+                                       int Tmax, void* x, int layer, int precision, void* stream);
+
 /* Backward of radtts_flowstep_forward (what PyTorch autograd derives for the reference).
  * Consumes the activation buffers the forward call filled (`fwd`) and a prepared blob built with
  * want_backward = 1.  Weight gradients are float32 in the reference's PyTorch layouts and are OVERWRITTEN. */

@@ -423,6 +423,36 @@ static int flowstep_entry(const radtts_flow_dims* dims, const void* prepared, co
     return flowstep_impl<__nv_bfloat16>(*dims, base, pv, *buf, inverse, (cudaStream_t)stream);
   return RADTTS_ERR_INVALID_ARG;
 }
+// One WN in_layer (dilated partial conv + softplus) in isolation: x[layer] -> x[layer + 1].  Profiling hook for the
+// dominant kernel of the step (bench.py times it with CUDA events; ncu captures it by name).
+template <typename T>
+static int wn_layer_impl(const radtts_flow_dims& d, const uint8_t* base, const PlanView& pv, void* xbuf, int layer,
+                         cudaStream_t st) {
+  FlowLayout L = flow_layout(d, sizeof(T) == 4 ? RADTTS_PREC_FP32 : RADTTS_PREC_BF16, 0);
+  const int nc = d.n_ch, k = d.ksize, rows = pv.rows_alloc;
+  RowMeta meta{pv.pos(), pv.rem()};
+  T* x = reinterpret_cast<T*>(xbuf);
+  GemmDesc g{};
+  g.rows_alloc = rows;
+  g.plan = pv.hdr();
+  g.nseg = k;
+  for (int t = 0; t < k; ++t) g.seg[t] = Seg{x + (size_t)layer * rows * nc, nc, (t - k / 2) << layer, 0, nc};
+  g.w = base + L.w_in[layer]; g.ldw = k * nc; g.N = nc;
+  EpiBiasAct<T> e{x + (size_t)(layer + 1) * rows * nc, nc, 0, reinterpret_cast<const float*>(base + L.b_in[layer]), meta,
+                  ACT_SOFTPLUS, d.partial_padding, layer, k, 1};
+  return run_gemm<T>(g, e, st);
+}
+extern "C" int radtts_wn_layer_forward(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
+                                       int Tmax, void* x, int layer, int precision, void* stream) {
+  RB_TRY(check_dims(dims));
+  if (!prepared || !plan || !x || layer < 0 || layer >= dims->n_layers) return RADTTS_ERR_INVALID_ARG;
+  PlanView pv = make_plan_view(plan, B, Tmax);
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(prepared);
+  if (precision == RADTTS_PREC_FP32) return wn_layer_impl<float>(*dims, base, pv, x, layer, (cudaStream_t)stream);
+  if (precision == RADTTS_PREC_BF16) return wn_layer_impl<__nv_bfloat16>(*dims, base, pv, x, layer, (cudaStream_t)stream);
+  return RADTTS_ERR_INVALID_ARG;
+}
+
 extern "C" int radtts_flowstep_forward(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
                                        int Tmax, const radtts_flow_buffers* buf, int precision, void* stream) {
   return flowstep_entry(dims, prepared, plan, B, Tmax, buf, precision, 0, stream);

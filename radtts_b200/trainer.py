@@ -1,0 +1,49 @@
+"""One optimisation step of RADTTS on the B200 hot path, mirroring the reference training loop body
+(reference train.py:385-422): forward under autocast -> RADTTSLoss (+ binarization loss) -> backward ->
+gradient all-reduce (DDP/NCCL) -> clip -> optimizer step."""
+import torch
+
+from . import loss as rloss
+
+
+class TrainStep:
+    def __init__(self, model, loss_weights, lr=1e-4, weight_decay=1e-6, grad_clip_val=1.0, bf16=True,
+                 binarize_attention=True, use_binarization_loss=True, ddp=False, device_ids=None):
+        self.raw_model = model
+        self.model = model
+        if ddp:
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            self.model = DDP(model, device_ids=device_ids, bucket_cap_mb=128, gradient_as_bucket_view=True)
+        self.criterion = rloss.RADTTSLoss(sigma=1.0, n_group_size=model.n_group_size, loss_weights=loss_weights)
+        self.bin_loss = rloss.AttentionBinarizationLoss()
+        self.loss_weights = loss_weights
+        self.bf16 = bf16
+        self.binarize = binarize_attention
+        self.use_bin_loss = use_binarization_loss
+        self.grad_clip_val = grad_clip_val
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.optimizer = torch.optim.RAdam(params, lr=lr, weight_decay=weight_decay, foreach=True)
+
+    def forward_loss(self, batch):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.bf16):
+            out = self.model(batch["mel"], batch["speaker_ids"], batch["text"], batch["in_lens"], batch["out_lens"],
+                             binarize_attention=self.binarize, attn_prior=batch["attn_prior"],
+                             f0=batch.get("f0"), energy_avg=batch.get("energy_avg"),
+                             voiced_mask=batch.get("voiced_mask"), p_voiced=batch.get("p_voiced"))
+            losses = self.criterion(out, batch["in_lens"], batch["out_lens"])
+            total = None
+            for v, w in losses.values():
+                if w > 0:
+                    total = v * w if total is None else total + v * w
+            if self.binarize and self.use_bin_loss:
+                total = total + self.bin_loss(out["attn"], out["attn_soft"]) * self.loss_weights["binarization_loss_weight"]
+        return total, out
+
+    def step(self, batch):
+        self.optimizer.zero_grad(set_to_none=True)
+        total, _ = self.forward_loss(batch)
+        total.backward()
+        if self.grad_clip_val > 0:
+            torch.nn.utils.clip_grad_norm_(self.raw_model.parameters(), self.grad_clip_val, foreach=True)
+        self.optimizer.step()
+        return total.detach()
