@@ -230,13 +230,28 @@ class Encoder(nn.Module):
             x = F.dropout(F.relu(conv(x)), 0.5, self.training)
         return x
 
+    def _convs_masked(self, x, in_lens):
+        """All utterances at once: the reference crops every utterance and runs the conv stack on it alone
+        (common.py:348-356); a length mask through the partial convs and the instance norms is the same math
+        without the Python loop over the batch."""
+        mask = get_mask_from_lengths(in_lens, x.shape[2])[:, None].to(x.dtype)
+        n = in_lens.to(x.dtype).clamp(min=1)[:, None, None]
+        for block in self.convolutions:
+            conv, norm = block[0], block[1]
+            y = conv(x, mask)
+            mean = (y * mask).sum(2, keepdim=True) / n
+            var = (((y - mean) * mask) ** 2).sum(2, keepdim=True) / n
+            y = (y - mean) * torch.rsqrt(var + norm.eps)
+            if norm.weight is not None:
+                y = y * norm.weight[None, :, None] + norm.bias[None, :, None]
+            x = F.dropout(F.relu(y), 0.5, self.training) * mask
+        return x
+
     def forward(self, x, in_lens):
         with torch.autocast(device_type=x.device.type, enabled=False):
             x = x.float()
             if x.shape[0] > 1:
-                pieces = [self._convs(x[b:b + 1, :, :int(in_lens[b])])[0].transpose(0, 1)
-                          for b in range(x.shape[0])]
-                x = nn.utils.rnn.pad_sequence(pieces, batch_first=True)
+                x = self._convs_masked(x, in_lens).transpose(1, 2)
             else:
                 x = self._convs(x).transpose(1, 2)
             packed = nn.utils.rnn.pack_padded_sequence(x, in_lens.int().cpu(), batch_first=True)

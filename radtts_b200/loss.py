@@ -80,7 +80,9 @@ class AttentionCTCLoss(nn.Module):
         B, _, T1, T2 = attn_logprob.shape
         lp = F.pad(attn_logprob[:, 0], (1, 0), value=self.blank_logprob)                 # (B, T1, T2+1)
         cls = torch.arange(T2 + 1, device=lp.device)[None, None, :]
-        lp = lp.masked_fill(cls > in_lens[:, None, None], float("-inf"))
+        # classes beyond key_len are excluded from the softmax; a large finite negative (exp underflows to exactly 0)
+        # instead of -inf keeps the CTC backward free of (-inf) - (-inf)
+        lp = lp.float().masked_fill(cls > in_lens[:, None, None], -1e4)
         lp = F.log_softmax(lp, dim=2).permute(1, 0, 2)                                   # (T1, B, T2+1)
         targets = torch.arange(1, T2 + 1, device=lp.device)[None, :].expand(B, -1)
         losses = F.ctc_loss(lp, targets, out_lens, in_lens, blank=0, reduction="none", zero_infinity=True)
