@@ -259,7 +259,9 @@ def main():
     if sampler:
         sampler.start()
     launches0 = _lib.launch_count()
+    torch.cuda.profiler.start()   # no-op unless run under `ncu --profile-from-start off` (profiles/ recipe)
     ms = time_region(step_resident, args.steps, world)
+    torch.cuda.profiler.stop()
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     frames_total = sum_over_ranks(frames_per_step_local, world)
