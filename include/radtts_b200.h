@@ -69,22 +69,26 @@ RADTTS_API int radtts_mas_forward(const float* attn, int is_prob, const int64_t*
  * layer (get_mask_from_lengths, reference common.py:86-97, called from common.py:567 etc.).  Here the
  * valid frames of all utterances are packed channels-last into one row axis with 16 zero rows between
  * utterances; the plan (row offsets, per-row position metadata) is built on the device from the lengths.
- *   lens     (B) int64 device; frames per utterance = lens[b] / divisor (clamped to [0, Tmax]).
+ *   lens     (B) int64 device; VALID frames per utterance = lens[b] / divisor (clamped to [0, Tmax]).
+ *   geom_lens NULL, or (B) int64: rows physically reserved per utterance (>= valid).  Needed only for plain
+ *            (non-partial) ConvNorm stacks, whose first layer reads the padded region too (common.py:145-154).
  *   plan     device buffer of radtts_frameplan_bytes(B, Tmax) bytes.
  *   rows     radtts_frameplan_rows(B, Tmax): allocated rows (multiple of 128) of every packed buffer.
  * ---------------------------------------------------------------------------------------------- */
 RADTTS_API size_t radtts_frameplan_bytes(int B, int Tmax);
 RADTTS_API int radtts_frameplan_rows(int B, int Tmax);
-RADTTS_API int radtts_frameplan_build(const int64_t* lens, int divisor, int B, int Tmax, void* plan, void* stream);
+RADTTS_API int radtts_frameplan_build(const int64_t* lens, const int64_t* geom_lens, int divisor, int B, int Tmax,
+                                      void* plan, void* stream);
 
 /* (B, C, T) float32  <->  packed rows.  Implements the reference's squeeze/unsqueeze
  * (nn.Unfold((g,1), stride g) reference radtts.py:165-169,414 and fold radtts.py:308-318) as pure indexing:
  * packed[row0[b] + t'][col_off + c*g + k] = x[b][c][g*t' + k].
  *   pack:   dst is float32 (dst_bf16 = 0) or bfloat16 (dst_bf16 = 1), row stride ld elements; columns
- *           [col_off, col_off + ncols_pad) are written (zeros beyond C*g and on gap rows).
+ *           [col_off, col_off + ncols_pad) are written (zeros beyond C*g and on gap rows; with valid_only = 1 also
+ *           on rows of the geometric span that lie past the valid length, i.e. the `x * mask` of a partial conv).
  *   unpack: src float32 packed, dst (B, C, Tmax*g) float32, zeros beyond each utterance's length. */
 RADTTS_API int radtts_pack_frames(const float* src, int B, int C, int T, int g, const void* plan, int Tmax, void* dst,
-                                  int dst_bf16, int ld, int col_off, int ncols_pad, void* stream);
+                                  int dst_bf16, int ld, int col_off, int ncols_pad, int valid_only, void* stream);
 RADTTS_API int radtts_unpack_frames(const float* src, int ld, int col_off, const void* plan, int B, int Tmax, int C,
                                     int g, float* dst, void* stream);
 
@@ -204,6 +208,34 @@ RADTTS_API int radtts_convattn_forward(const float* q_enc, const float* k_enc, c
 RADTTS_API int radtts_convattn_backward(const float* q_enc, const float* k_enc, const float* lse, const float* attn,
                                         const float* g_attn, const float* g_logprob, int has_prior, int B, int C, int T1,
                                         int T2, float temp, float* gd_ws, float* g_q, float* g_k, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attribute flows (BGAP, config_ljs_bgap): SimpleConvNet layers, RQ-spline / affine coupling, tiny 1x1 conv.
+ * ---------------------------------------------------------------------------------------------- */
+/* One ConvNorm layer on packed rows (reference common.py:145-154 with partialconv1d.py:35-71 when partial = 1):
+ * y = act(ratio * conv_k,dil(x) + bias) on valid rows, zeros on gap rows when mask_rows = 1.
+ * act: 0 none, 1 softplus, 2 relu.  x: act [rows][ld_x] (first c_in_pad columns, c_in_pad % 64 == 0, zero padded);
+ * y: act [rows][ld_y], columns [y_col_off, y_col_off + round_up(c_out, 16)) are written.
+ * The weight (c_out, c_in, ksize) float32 is re-laid out once by radtts_conv_prepare. */
+RADTTS_API size_t radtts_conv_prepared_bytes(int c_out, int c_in_pad, int ksize, int precision);
+RADTTS_API int radtts_conv_prepare(const float* w, const float* bias, int c_out, int c_in, int c_in_pad, int ksize,
+                                   int precision, void* prepared, size_t prepared_bytes, void* stream);
+RADTTS_API int radtts_conv_rows(const void* prepared, int c_out, int c_in_pad, int ksize, int dilation, int act,
+                                int partial, int mask_rows, const void* x, int ld_x, void* y, int ld_y, int y_col_off,
+                                const void* plan, int B, int Tmax, int precision, void* stream);
+/* Rational-quadratic spline coupling transform (reference splines.py:221-319 through
+ * SplineTransformationLayer.forward, common.py:699-743), (B, C, T) float32 tensors:
+ * x: coupling input (first C/2 channels pass through, last C/2 are transformed); params (B, C/2 * (2 n_bins + 1), T)
+ * = SimpleConvNet output; inverse = 1 for sampling.  y (B, C, T); log_s (B, T) (forward only, may be NULL). */
+RADTTS_API int radtts_rqspline_apply(const float* x, const float* params, int B, int C, int T, int n_bins, int inverse,
+                                     float left, float right, float bottom, float top, float* y, float* log_s,
+                                     void* stream);
+/* Affine coupling apply (reference common.py:782-784,821-832): params (B, C, T) = [raw scale | translation];
+ * scaling 0 tanh, 1 exp, 2 sigmoid, 3 translate.  log_s (B, C/2, T) forward only, may be NULL. */
+RADTTS_API int radtts_affine_apply(const float* z, const float* params, int B, int C, int T, int scaling, int inverse,
+                                   float* y, float* log_s, void* stream);
+/* y[b,:,t] = W x[b,:,t] for a small dense W (C <= 16): the plain Invertible1x1Conv of BGAP (common.py:431-472). */
+RADTTS_API int radtts_pointwise_conv_small(const float* x, const float* w, int B, int C, int T, float* y, void* stream);
 
 #ifdef __cplusplus
 }

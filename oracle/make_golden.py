@@ -171,7 +171,57 @@ def gen_radtts_forward(ns):
           "loss_mel %.5f ctc %.5f bin %.5f" % (g["loss_mel"], g["loss_ctc"], g["loss_binarization"]))
 
 
-GENERATORS = {"mas": gen_mas, "radtts_forward": gen_radtts_forward}
+def gen_bgap(ns):
+    """config_ljs_bgap: the two BGAP attribute flows (F0: group 2, energy: group 4), sampling (infer) and training
+    (forward) directions, straight through the reference modules (attribute_prediction_model.py:187-224)."""
+    import torch
+    model, cfg, sd = _ref_model(ns, "config_ljs_bgap.json")
+    rng = np.random.default_rng(777)
+    B, T = 3, 48
+    lens = torch.tensor([48, 36, 28])
+    txt = rng.standard_normal((B, 512, T), dtype=np.float32) * 0.5
+    for b in range(B):
+        txt[b, :, int(lens[b]):] = 0
+    txt = torch.from_numpy(txt)
+    spk = torch.from_numpy(rng.standard_normal((B, 16), dtype=np.float32) * 0.3)
+    g = {"txt": txt.numpy(), "spk": spk.numpy(), "lens": lens.numpy()}
+    for name, mod in (("f0", model.f0_pred_module), ("energy", model.energy_pred_module)):
+        z = torch.from_numpy(rng.standard_normal((B, 2, T), dtype=np.float32) * 0.8)
+        x = torch.from_numpy(rng.standard_normal((B, 2, T), dtype=np.float32) * 0.9)
+        with torch.no_grad():
+            x_hat = mod.infer(z, txt, spk, lens)
+            out = mod(txt, spk, x, lens)
+        g[name + "_z_in"] = z.numpy()
+        g[name + "_x_hat"] = x_hat.numpy()
+        g[name + "_x_in"] = x.numpy()
+        g[name + "_z_out"] = out["z"].numpy()
+        g[name + "_log_det_W"] = np.array([float(v) for v in out["log_det_W_list"]], dtype=np.float32)
+        for i, ls in enumerate(out["log_s_list"]):
+            g[name + "_log_s_%d" % i] = ls.numpy()
+    np.savez_compressed(os.path.join(GOLD, "bgap.npz"), **g)
+    print("wrote bgap.npz", os.path.getsize(os.path.join(GOLD, "bgap.npz")), "bytes")
+
+
+def gen_decoder_cfg_forward(ns):
+    """config_ljs_decoder (RADTTS++ decoder conditioned on F0 / energy / voicing): full forward in eval mode."""
+    import torch
+    from radtts_b200 import synth
+    model, cfg, sd = _ref_model(ns, "config_ljs_decoder.json")
+    B, T1, T2 = 2, 60, 20
+    batch = synth.synth_batch(B, T1, T2, seed=4321, with_attributes=True)
+    with torch.no_grad():
+        out = model(batch["mel"], batch["speaker_ids"], batch["text"], batch["in_lens"], batch["out_lens"],
+                    binarize_attention=True, attn_prior=batch["attn_prior"], f0=batch["f0"],
+                    energy_avg=batch["energy_avg"], voiced_mask=batch["voiced_mask"], p_voiced=batch["p_voiced"])
+    g = {"z_mel": out["z_mel"].numpy(), "attn": out["attn"].numpy(), "attn_soft": out["attn_soft"].numpy(),
+         "log_det_W": np.array([float(x) for x in out["log_det_W_list"]], dtype=np.float32),
+         "log_s_0": out["log_s_list"][0].numpy(), "log_s_7": out["log_s_list"][7].numpy()}
+    np.savez_compressed(os.path.join(GOLD, "decoder_cfg_forward.npz"), **g)
+    print("wrote decoder_cfg_forward.npz", os.path.getsize(os.path.join(GOLD, "decoder_cfg_forward.npz")), "bytes")
+
+
+GENERATORS = {"mas": gen_mas, "radtts_forward": gen_radtts_forward, "bgap": gen_bgap,
+              "decoder_cfg_forward": gen_decoder_cfg_forward}
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)

@@ -15,32 +15,42 @@ namespace rb {
 // ====================================================================================================
 // frame plan
 // ====================================================================================================
-__global__ void __launch_bounds__(1024) frameplan_kernel(const int64_t* __restrict__ lens, int divisor, int B,
-                                                         int Tmax, int rows_alloc, int* __restrict__ plan) {
+__global__ void __launch_bounds__(1024) frameplan_kernel(const int64_t* __restrict__ lens, const int64_t* __restrict__ geom_lens,
+                                                         int divisor, int B, int Tmax, int rows_alloc,
+                                                         int* __restrict__ plan) {
   int* hdr = plan;
   int* row0 = plan + 8;
   int* len = plan + 8 + B;
+  int* glen = plan + 8 + 2 * B;
   int* pos = plan + plan_meta_off(B);
   int* rem = pos + rows_alloc;
   int* utt = rem + rows_alloc;
+  int* tpos = utt + rows_alloc;
   const int tid = threadIdx.x;
   if (tid == 0) {
     int r = kGap;
     for (int b = 0; b < B; ++b) {
       long long l = lens[b] / divisor;
       int li = (int)(l < 0 ? 0 : (l > Tmax ? Tmax : l));
+      long long gl = geom_lens ? geom_lens[b] / divisor : l;
+      int gi = (int)(gl < li ? li : (gl > Tmax ? Tmax : gl));
       row0[b] = r;
       len[b] = li;
-      r += li + kGap;
+      glen[b] = gi;
+      r += gi + kGap;
     }
     hdr[0] = r;  // rows in use (ends with a gap)
     hdr[1] = B; hdr[2] = Tmax; hdr[3] = rows_alloc; hdr[4] = hdr[5] = hdr[6] = hdr[7] = 0;
   }
-  for (int i = tid; i < rows_alloc; i += blockDim.x) { pos[i] = -1; rem[i] = -1; utt[i] = -1; }
+  for (int i = tid; i < rows_alloc; i += blockDim.x) { pos[i] = -1; rem[i] = -1; utt[i] = -1; tpos[i] = -1; }
   __syncthreads();
   for (int b = 0; b < B; ++b) {
-    const int r0 = row0[b], l = len[b];
-    for (int t = tid; t < l; t += blockDim.x) { pos[r0 + t] = t; rem[r0 + t] = l - 1 - t; utt[r0 + t] = b; }
+    const int r0 = row0[b], l = len[b], gl = glen[b];
+    for (int t = tid; t < gl; t += blockDim.x) {
+      utt[r0 + t] = b;
+      tpos[r0 + t] = t;
+      if (t < l) { pos[r0 + t] = t; rem[r0 + t] = l - 1 - t; }
+    }
   }
 }
 
@@ -50,15 +60,16 @@ __global__ void __launch_bounds__(1024) frameplan_kernel(const int64_t* __restri
 template <typename T>
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, int C, int Tsrc, int g,
                                                    PlanView pv, T* __restrict__ dst, int ld, int col_off,
-                                                   int ncols_pad) {
+                                                   int ncols_pad, int valid_only) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;  // all rows_alloc rows are written (zeros off-range)
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int ncols = C * g;
   {
     const int row = r0 + tx;
-    const int b = row < pv.rows_alloc ? pv.utt()[row] : -1;
-    const int t = b >= 0 ? pv.pos()[row] : 0;
+    int b = row < pv.rows_alloc ? pv.utt()[row] : -1;
+    if (valid_only && b >= 0 && pv.pos()[row] < 0) b = -1;  // inside the geometric span but past the valid length
+    const int t = b >= 0 ? pv.tpos()[row] : 0;
     for (int cc = ty; cc < 32; cc += 8) {
       const int col = c0 + cc;
       float v = 0.f;
@@ -88,7 +99,7 @@ __global__ void __launch_bounds__(256) unpack_kernel(const float* __restrict__ s
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int ncols = C * g;
-  const int len = pv.len()[b], row0 = pv.row0()[b];
+  const int len = pv.glen()[b], row0 = pv.row0()[b];  // geometric span (== valid length unless geom_lens given)
   const int Tout = pv.Tmax * g;
   for (int rr = ty; rr < 32; rr += 8) {
     const int t = t0 + rr, col = c0 + tx;
@@ -361,24 +372,25 @@ extern "C" int radtts_frameplan_rows(int B, int Tmax) {
   if (B <= 0 || Tmax <= 0) return 0;
   return plan_rows_alloc(B, Tmax);
 }
-extern "C" int radtts_frameplan_build(const int64_t* lens, int divisor, int B, int Tmax, void* plan, void* stream) {
+extern "C" int radtts_frameplan_build(const int64_t* lens, const int64_t* geom_lens, int divisor, int B, int Tmax,
+                                      void* plan, void* stream) {
   if (!lens || !plan || B <= 0 || Tmax <= 0 || divisor <= 0) return RADTTS_ERR_INVALID_ARG;
-  frameplan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lens, divisor, B, Tmax, plan_rows_alloc(B, Tmax),
+  frameplan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lens, geom_lens, divisor, B, Tmax, plan_rows_alloc(B, Tmax),
                                                         reinterpret_cast<int*>(plan));
   return after_launch();
 }
 
 extern "C" int radtts_pack_frames(const float* src, int B, int C, int T, int g, const void* plan, int Tmax, void* dst,
-                                  int dst_bf16, int ld, int col_off, int ncols_pad, void* stream) {
+                                  int dst_bf16, int ld, int col_off, int ncols_pad, int valid_only, void* stream) {
   if (!src || !plan || !dst || B <= 0 || C <= 0 || T <= 0 || g <= 0 || ncols_pad < C * g) return RADTTS_ERR_INVALID_ARG;
   PlanView pv = make_plan_view(plan, B, Tmax);
   dim3 grid(pv.rows_alloc / 32, ceil_div(ncols_pad, 32));
   if (dst_bf16)
     pack_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, C, T, g, pv, reinterpret_cast<__nv_bfloat16*>(dst),
-                                                                       ld, col_off, ncols_pad);
+                                                                       ld, col_off, ncols_pad, valid_only);
   else
     pack_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(src, C, T, g, pv, reinterpret_cast<float*>(dst), ld,
-                                                               col_off, ncols_pad);
+                                                               col_off, ncols_pad, valid_only);
   return after_launch();
 }
 extern "C" int radtts_unpack_frames(const float* src, int ld, int col_off, const void* plan, int B, int Tmax, int C,

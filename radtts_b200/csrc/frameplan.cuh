@@ -10,8 +10,10 @@
 // only ever land on zero rows, never on a neighbour.  Row metadata lets epilogues recover the position of a
 // row inside its utterance (for the partial-conv renormalisation) without any host synchronisation.
 //
-// int32 plan buffer:  hdr[8] = {rows_used, B, Tmax, rows_alloc, 0,0,0,0}; row0[B]; len[B]; pad to 4;
-//                     pos[rows_alloc]; rem[rows_alloc]; utt[rows_alloc]
+// int32 plan buffer:  hdr[8] = {rows_used, B, Tmax, rows_alloc, 0,0,0,0}; row0[B]; len[B]; glen[B]; pad to 4;
+//                     pos[rows_alloc]; rem[rows_alloc]; utt[rows_alloc]; tpos[rows_alloc]
+// pos/rem describe VALID frames (-1 elsewhere); utt/tpos describe the geometric span of an utterance, which may be
+// longer than its valid length when a layer must see the padded region too (plain, non-partial convs).
 #pragma once
 #include "common.cuh"
 
@@ -21,9 +23,9 @@ constexpr int kGap = 16;
 constexpr int kRowTile = 128;
 
 __host__ __device__ inline int plan_rows_alloc(int B, int Tmax) { return round_up(B * (Tmax + kGap) + kGap, kRowTile); }
-__host__ __device__ inline int plan_meta_off(int B) { return round_up(8 + 2 * B, 4); }
+__host__ __device__ inline int plan_meta_off(int B) { return round_up(8 + 3 * B, 4); }
 __host__ __device__ inline size_t plan_ints(int B, int Tmax) {
-  return (size_t)plan_meta_off(B) + 3 * (size_t)plan_rows_alloc(B, Tmax);
+  return (size_t)plan_meta_off(B) + 4 * (size_t)plan_rows_alloc(B, Tmax);
 }
 
 struct PlanView {
@@ -32,9 +34,11 @@ struct PlanView {
   __host__ __device__ const int* hdr() const { return base; }
   __host__ __device__ const int* row0() const { return base + 8; }
   __host__ __device__ const int* len() const { return base + 8 + B; }
+  __host__ __device__ const int* glen() const { return base + 8 + 2 * B; }
   __host__ __device__ const int* pos() const { return base + plan_meta_off(B); }
   __host__ __device__ const int* rem() const { return pos() + rows_alloc; }
   __host__ __device__ const int* utt() const { return rem() + rows_alloc; }
+  __host__ __device__ const int* tpos() const { return utt() + rows_alloc; }
 };
 
 inline PlanView make_plan_view(const void* plan, int B, int Tmax) {

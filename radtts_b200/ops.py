@@ -86,7 +86,7 @@ def unsqueeze_time(z, g):
 class FramePlan:
     """Device-side description of the packed frame layout (see csrc/frameplan.cuh)."""
 
-    def __init__(self, lens, divisor, tmax):
+    def __init__(self, lens, divisor, tmax, geom_lens=None):
         _lib.require_cuda(lens)
         L = _lib.lib()
         self.B = int(lens.shape[0])
@@ -96,8 +96,10 @@ class FramePlan:
         nbytes = int(L.radtts_frameplan_bytes(self.B, self.Tmax))
         self.buf = torch.empty(nbytes // 4, dtype=torch.int32, device=lens.device)
         self.lens = lens.to(torch.int64).contiguous()
-        _lib.check(L.radtts_frameplan_build(_lib.ptr(self.lens), self.divisor, self.B, self.Tmax,
-                                            _lib.ptr(self.buf), _lib.stream_of(lens)), "radtts_frameplan_build")
+        self.geom_lens = None if geom_lens is None else geom_lens.to(device=lens.device, dtype=torch.int64).contiguous()
+        _lib.check(L.radtts_frameplan_build(_lib.ptr(self.lens), _lib.ptr(self.geom_lens), self.divisor, self.B,
+                                            self.Tmax, _lib.ptr(self.buf), _lib.stream_of(lens)),
+                   "radtts_frameplan_build")
 
     @property
     def ptr(self):
@@ -107,7 +109,7 @@ class FramePlan:
         return torch.div(self.lens, self.divisor, rounding_mode="floor").clamp(0, self.Tmax)
 
 
-def pack_frames(src, plan, g, dtype=torch.float32, ld=None, col_off=0, ncols_pad=None, out=None):
+def pack_frames(src, plan, g, dtype=torch.float32, ld=None, col_off=0, ncols_pad=None, out=None, valid_only=False):
     """(B, C, T) fp32 -> packed [rows][ld]; columns [col_off, col_off + ncols_pad) are written."""
     _lib.require_cuda(src)
     src = src.float().contiguous()
@@ -120,7 +122,8 @@ def pack_frames(src, plan, g, dtype=torch.float32, ld=None, col_off=0, ncols_pad
             else torch.empty((plan.rows, ld), dtype=dtype, device=src.device)
     L = _lib.lib()
     _lib.check(L.radtts_pack_frames(_lib.ptr(src), B, C, T, g, plan.ptr, plan.Tmax, _lib.ptr(out),
-                                    int(out.dtype == torch.bfloat16), ld, col_off, ncols_pad, _lib.stream_of(src)),
+                                    int(out.dtype == torch.bfloat16), ld, col_off, ncols_pad, int(valid_only),
+                                    _lib.stream_of(src)),
                "radtts_pack_frames")
     return out
 
@@ -449,24 +452,133 @@ def decoder_inverse(model, residual, context, out_lens):
 # ------------------------------------------------------------------------------------------------------
 # remaining hot-path entry points (filled in as their kernels land)
 # ------------------------------------------------------------------------------------------------------
+def _no_grad_only(name, *tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError("%s: the training (backward) direction of the BGAP attribute flows is not built yet; "
+                                  "run it under torch.no_grad() (inference)" % name)
+
+
 def pointwise_conv(z, w):
-    raise NotImplementedError
+    """y[b,:,t] = W z[b,:,t] (Invertible1x1Conv / Invertible1x1ConvLUS module API on reference-shaped tensors)."""
+    _lib.require_cuda(z, w)
+    _no_grad_only("pointwise_conv", z, w)
+    z = z.float().contiguous()
+    w = w.detach().float().contiguous()
+    B, C, T = z.shape
+    if C > 16:
+        return torch.matmul(w, z)   # large-C 1x1 convs on the hot path go through ops.flow_step instead
+    y = torch.empty_like(z)
+    _lib.check(_lib.lib().radtts_pointwise_conv_small(_lib.ptr(z), _lib.ptr(w), B, C, T, _lib.ptr(y), _lib.stream_of(z)),
+               "radtts_pointwise_conv_small")
+    return y
 
 
 def wn_forward(wn, z, context, seq_lens):
     raise NotImplementedError("WN runs fused inside FlowStep (ops.flow_step); standalone WN.forward is not exposed")
 
 
-def affine_coupling(layer, z, context, inverse, seq_lens):
-    raise NotImplementedError
+_conv_cache = {}
+
+
+def _prepared_conv(conv, c_in_pad, prec):
+    """Re-laid-out weight blob of a Conv1d (cached per parameter version: inference weights are frozen)."""
+    w, b = conv.weight, conv.bias
+    key = (id(conv), w._version, None if b is None else b._version, c_in_pad, prec, w.device.index)
+    hit = _conv_cache.get(id(conv))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    L = _lib.lib()
+    c_out, c_in, k = w.shape
+    nbytes = int(L.radtts_conv_prepared_bytes(c_out, c_in_pad, k, prec))
+    blob = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    wf = w.detach().float().contiguous()
+    bf = None if b is None else b.detach().float().contiguous()
+    _lib.check(L.radtts_conv_prepare(_lib.ptr(wf), _lib.ptr(bf), c_out, c_in, c_in_pad, k, prec, _lib.ptr(blob),
+                                     ctypes.c_size_t(nbytes), _lib.stream_of(w)), "radtts_conv_prepare")
+    _conv_cache[id(conv)] = (key, blob)
+    return blob
+
+
+def _pad64(n):
+    return (n + 63) // 64 * 64
 
 
 def simple_conv_net(net, x, seq_lens):
-    raise NotImplementedError
+    """SimpleConvNet.forward (reference common.py:503-515) on packed rows: n_layers x [ConvNorm (+partial padding) ->
+    ReLU] then the 1x1 `last_layer`; every layer is one row-GEMM launch with a fused epilogue."""
+    _lib.require_cuda(x)
+    _no_grad_only("SimpleConvNet", x, *net.parameters())
+    B, C, T = x.shape
+    prec = current_precision()
+    act = _act_dtype(prec)
+    dev = x.device
+    if seq_lens is None:
+        seq_lens = torch.full((B,), T, dtype=torch.int64, device=dev)
+    # The reference runs these nets over the whole zero-padded batch: plain (non-partial) ConvNorm layers read the
+    # padded region in their first layer and `last_layer` is not masked (common.py:145-154,514), so values in the
+    # padded region feed back into valid frames of later flows.  To stay identical, every utterance physically keeps
+    # all T rows; validity (the `* mask` after each ConvNorm, the partial-conv counts) still follows seq_lens.
+    geom = torch.full((B,), T, dtype=torch.int64, device=dev)
+    plan = FramePlan(seq_lens.to(dev), 1, T, geom)
+    L = _lib.lib()
+    stream = _lib.stream_of(x)
+    lease = _Lease()
+    cur = pack_frames(x, plan, 1, act, _pad64(C), 0, _pad64(C), valid_only=bool(net.use_partial_padding))
+    cur_w = _pad64(C)
+    convs = [(layer.conv, layer.dilation, 2, int(net.use_partial_padding)) for layer in net.layers]
+    convs.append((net.last_layer, 1, 0, 0))
+    for i, (conv, dil, act_code, partial) in enumerate(convs):
+        mask_rows = 0 if i == len(convs) - 1 else 1
+        c_out, c_in, k = conv.weight.shape
+        blob = _prepared_conv(conv, cur_w, prec)
+        out_w = _pad64(c_out)
+        out = lease.take("y%d" % i, (plan.rows, out_w), act, dev)
+        _lib.check(L.radtts_conv_rows(_lib.ptr(blob), c_out, cur_w, k, dil, act_code, partial, mask_rows, _lib.ptr(cur), cur_w,
+                                      _lib.ptr(out), out_w, 0, plan.ptr, plan.B, plan.Tmax, prec, stream),
+                   "radtts_conv_rows")
+        cur, cur_w = out, out_w
+    res = unpack_frames(cur.float() if cur.dtype != torch.float32 else cur, plan, convs[-1][0].weight.shape[0], 1, 0)
+    lease.release()
+    return res
+
+
+def affine_coupling(layer, z, context, inverse, seq_lens):
+    """AffineTransformationLayer.forward (reference common.py:810-832) on reference-shaped tensors."""
+    if layer.affine_model == "wavenet":
+        raise NotImplementedError("the WN-based coupling runs fused inside FlowStep (ops.flow_step)")
+    _lib.require_cuda(z, context)
+    _no_grad_only("AffineTransformationLayer", z, context)
+    scaling = layer.scaling_fn
+    if isinstance(scaling, list) or scaling not in _SCALING:
+        raise NotImplementedError("per-channel scaling_fn lists are not supported")
+    z = z.float().contiguous()
+    B, C, T = z.shape
+    h = C // 2
+    params = simple_conv_net(layer.affine_param_predictor, torch.cat((z[:, :h], context.float()), 1), seq_lens)
+    y = torch.empty_like(z)
+    log_s = None if inverse else torch.empty((B, h, T), dtype=torch.float32, device=z.device)
+    _lib.check(_lib.lib().radtts_affine_apply(_lib.ptr(z), _lib.ptr(params.contiguous()), B, C, T, _SCALING[scaling],
+                                              int(bool(inverse)), _lib.ptr(y), _lib.ptr(log_s), _lib.stream_of(z)),
+               "radtts_affine_apply")
+    return y if inverse else (y, log_s)
 
 
 def spline_coupling(layer, z, context, inverse, seq_lens):
-    raise NotImplementedError
+    """SplineTransformationLayer.forward with use_quadratic=True (reference common.py:694-743, splines.py:221-319)."""
+    _lib.require_cuda(z, context)
+    _no_grad_only("SplineTransformationLayer", z, context)
+    z = z.float().contiguous()
+    B, C, T = z.shape
+    h = layer.half_mel_channels
+    params = simple_conv_net(layer.param_predictor, torch.cat((z[:, :h], context.float()), 1), seq_lens).contiguous()
+    n_bins = layer.n_bins // 2
+    y = torch.empty_like(z)
+    log_s = None if inverse else torch.empty((B, 1, T), dtype=torch.float32, device=z.device)
+    _lib.check(_lib.lib().radtts_rqspline_apply(_lib.ptr(z), _lib.ptr(params), B, C, T, n_bins, int(bool(inverse)),
+                                                ctypes.c_float(layer.left), ctypes.c_float(layer.right),
+                                                ctypes.c_float(layer.bottom), ctypes.c_float(layer.top), _lib.ptr(y),
+                                                _lib.ptr(log_s), _lib.stream_of(z)), "radtts_rqspline_apply")
+    return y if inverse else (y, log_s)
 
 
 class _ConvAttnFn(torch.autograd.Function):

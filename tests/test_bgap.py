@@ -1,0 +1,80 @@
+"""BGAP attribute flows (config_ljs_bgap): the CPU oracle against reference goldens (CPU test) and
+the CUDA path -- SimpleConvNet row-GEMMs, RQ-spline / affine coupling kernels, small 1x1 conv -- against the same
+goldens (GPU test)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flow as oflow
+from radtts_b200 import configs, synth
+from radtts_b200.radtts import RADTTS
+
+GROUP = {"f0": 2, "energy": 4}
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "bgap.npz"))
+
+
+@pytest.fixture(scope="module")
+def model_and_sd():
+    torch.manual_seed(0)
+    m = RADTTS(**configs.model_config("bgap")).eval()
+    sd = synth.load_synth(m, seed=1234)
+    return m, sd
+
+
+def _valid(x, lens):
+    m = (torch.arange(x.shape[-1])[None, :] < lens[:, None]).to(x.dtype)
+    return x * m[:, None]
+
+
+@pytest.mark.parametrize("name", ["f0", "energy"])
+def test_oracle_bgap_matches_reference(gold, model_and_sd, name):
+    _, sd = model_and_sd
+    g = GROUP[name]
+    txt, spk, lens = torch.from_numpy(gold["txt"]), torch.from_numpy(gold["spk"]), torch.from_numpy(gold["lens"])
+    prefix = "%s_pred_module." % name
+    with torch.no_grad():
+        x_hat = oflow.bgap_infer(sd, prefix, torch.from_numpy(gold[name + "_z_in"]), txt, spk, lens, n_group=g)
+        z, logdets, log_s = oflow.bgap_forward(sd, prefix, torch.from_numpy(gold[name + "_x_in"]), txt, spk, lens,
+                                               n_group=g)
+    ref = torch.from_numpy(gold[name + "_x_hat"])
+    assert torch.allclose(_valid(x_hat, lens), _valid(ref, lens), rtol=1e-3, atol=1e-4)
+    assert torch.allclose(_valid(z, lens // g), _valid(torch.from_numpy(gold[name + "_z_out"]), lens // g), rtol=1e-3,
+                          atol=1e-4)
+    assert np.allclose(np.array([float(v) for v in logdets]), gold[name + "_log_det_W"], rtol=1e-4, atol=1e-5)
+    for i, ls in enumerate(log_s):
+        want = torch.from_numpy(gold[name + "_log_s_%d" % i])
+        assert torch.allclose(_valid(ls, lens // g), _valid(want, lens // g), rtol=1e-3, atol=1e-4), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["f0", "energy"])
+def test_cuda_bgap_infer_and_forward_match_reference(gold, model_and_sd, name, cuda_lib):
+    from radtts_b200 import ops
+    model, _ = model_and_sd
+    mod = getattr(model, name + "_pred_module").cuda()
+    g = GROUP[name]
+    txt, spk = torch.from_numpy(gold["txt"]).cuda(), torch.from_numpy(gold["spk"]).cuda()
+    lens = torch.from_numpy(gold["lens"]).cuda()
+    ops.set_precision("fp32")
+    try:
+        with torch.no_grad():
+            x_hat = mod.infer(torch.from_numpy(gold[name + "_z_in"]).cuda(), txt, spk, lens)
+            out = mod(txt, spk, torch.from_numpy(gold[name + "_x_in"]).cuda(), lens)
+    finally:
+        ops.set_precision(None)
+    lc = lens.cpu()
+    assert torch.allclose(_valid(x_hat.cpu(), lc), _valid(torch.from_numpy(gold[name + "_x_hat"]), lc), rtol=1e-3,
+                          atol=2e-4)
+    assert torch.allclose(_valid(out["z"].cpu(), lc // g), _valid(torch.from_numpy(gold[name + "_z_out"]), lc // g),
+                          rtol=1e-3, atol=2e-4)
+    assert np.allclose(np.array([float(v) for v in out["log_det_W_list"]]), gold[name + "_log_det_W"], rtol=1e-4,
+                       atol=1e-5)
+    for i, ls in enumerate(out["log_s_list"]):
+        want = torch.from_numpy(gold[name + "_log_s_%d" % i])
+        assert torch.allclose(_valid(ls.cpu(), lc // g), _valid(want, lc // g), rtol=1e-3, atol=2e-4), i

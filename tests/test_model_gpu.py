@@ -93,3 +93,34 @@ def test_train_step_runs_and_all_hot_path_params_get_grads(model):
     finally:
         model.eval()
         ops.set_precision(None)
+
+
+def test_decoder_config_forward_matches_reference(golden_dir, cuda_lib):
+    """config_ljs_decoder (cfg3): decoder conditioned on F0 / energy / voicing -- full forward vs reference golden."""
+    g = np.load(os.path.join(golden_dir, "decoder_cfg_forward.npz"))
+    torch.manual_seed(0)
+    m = RADTTS(**configs.model_config("decoder")).eval()
+    synth.load_synth(m, seed=1234)
+    m = m.cuda()
+    b = {k: v.cuda() for k, v in synth.synth_batch(2, 60, 20, seed=4321, with_attributes=True).items()}
+    ops.set_precision("fp32")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            out = m(b["mel"], b["speaker_ids"], b["text"], b["in_lens"], b["out_lens"], binarize_attention=True,
+                    attn_prior=b["attn_prior"], f0=b["f0"], energy_avg=b["energy_avg"], voiced_mask=b["voiced_mask"],
+                    p_voiced=b["p_voiced"])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        ops.set_precision(None)
+    assert torch.allclose(out["attn_soft"].cpu(), torch.from_numpy(g["attn_soft"]), rtol=1e-3, atol=1e-6)
+    assert np.array_equal(out["attn"].cpu().numpy(), g["attn"])
+    lens = b["out_lens"] // 2
+    assert torch.allclose(_valid(out["z_mel"], lens).cpu(), _valid(torch.from_numpy(g["z_mel"]), lens.cpu()), rtol=1e-3,
+                          atol=3e-4)
+    assert np.allclose(np.array([float(x) for x in out["log_det_W_list"]]), g["log_det_W"], rtol=1e-4, atol=1e-5)
+    for i in (0, 7):
+        assert torch.allclose(_valid(out["log_s_list"][i], lens).cpu(),
+                              _valid(torch.from_numpy(g["log_s_%d" % i]), lens.cpu()), rtol=1e-3, atol=1e-5)
