@@ -204,15 +204,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * kTcMaxBN + ((uint32_t)(quad * 32) << 16);
-      for (int c = 0; c < p.bn; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_addr + c, r);
-        tmem_ld_wait();
-        if (n0 + c < p.N) {  // rows past the packed range are gap rows: functors write zeros there
-          float v[16];
+      // TMEM -> registers in 64-column groups, software pipelined: the tcgen05.ld of group g+1 is in flight while
+      // group g runs through the epilogue functor (a lone ld + wait per 16 columns costs a full TMEM round trip
+      // each time and made the epilogue, not the MMAs, the critical path of the K = 1024 GEMMs).
+      uint32_t ra[4][16], rbuf[4][16];
+      const int ngroups = (p.bn + 63) / 64;
+      auto load_group = [&](uint32_t (&dst)[4][16], int g) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-          epi.template operator()<16>(row, n0 + c, v);
+        for (int q = 0; q < 4; ++q)
+          if (g * 64 + q * 16 < p.bn) tmem_ld16(t_addr + g * 64 + q * 16, dst[q]);
+      };
+      auto run_group = [&](uint32_t (&src)[4][16], int g) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = g * 64 + q * 16;
+          if (c < p.bn && n0 + c < p.N) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(src[q][i]);
+            epi.template operator()<16>(row, n0 + c, v);
+          }
+        }
+      };
+      load_group(ra, 0);
+      for (int g = 0; g < ngroups; g += 2) {
+        tmem_ld_wait();
+        if (g + 1 < ngroups) load_group(rbuf, g + 1);
+        run_group(ra, g);
+        if (g + 1 < ngroups) {
+          tmem_ld_wait();
+          if (g + 2 < ngroups) load_group(ra, g + 2);
+          run_group(rbuf, g + 1);
         }
       }
       tc_fence_before();
