@@ -120,8 +120,20 @@ struct RowMeta {
   }
 };
 
+// Per-row state an epilogue needs (validity, partial-conv ratio): computed ONCE per row per tile and kept in
+// registers -- re-reading pos/rem from global memory for every 16-column chunk put a full memory round trip on
+// the epilogue's critical path (ncu: 80 % of epilogue stalls were long-scoreboard on exactly these loads).
+struct RowState {
+  bool ok;
+  float rt;
+};
+
 // ------------------------------------------------------------------------------------------------------
-// epilogue functors:  template<int W> void operator()(int row, int col0, const float (&acc)[W])
+// epilogue functors:
+//   RowState prep(int row)                                  once per row per tile
+//   const float* colvec()                                   per-column vector (bias) the engine stages per tile, or null
+//   template<int W> void operator()(int row, int col0, const float (&acc)[W], const RowState& rs, const float* cv)
+//        cv[i] = colvec()[col0 + i]  (already offset to the chunk)
 // `row` < rows in use, col0 % W == 0, col0 + W <= round_up(N, W); functors guard col < N themselves when
 // their N is not a multiple of W.
 // ------------------------------------------------------------------------------------------------------
@@ -137,14 +149,22 @@ struct EpiBiasAct {
   int partial;       // 1: multiply acc by the partial-conv ratio
   int log2d, ksize;
   int mask_rows;     // 1: zero gap rows; 0: plain conv (ConvAttention projections)
+  __device__ __forceinline__ RowState prep(int row) const {
+    RowState rs;
+    rs.ok = !mask_rows || meta.valid(row);
+    rs.rt = (partial && rs.ok) ? meta.ratio(row, log2d, ksize) : 1.f;
+    return rs;
+  }
+  __device__ __forceinline__ const float* colvec() const { return bias; }
   template <int W>
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W]) const {
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
+                                             const float* cv) const {
     float y[W];
-    const bool ok = !mask_rows || meta.valid(row);
-    const float rt = (partial && ok) ? meta.ratio(row, log2d, ksize) : 1.f;
+    const bool ok = rs.ok;
+    const float rt = rs.rt;
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-      float v = acc[i] * rt + bias[col0 + i];
+      float v = acc[i] * rt + cv[i];
       if (act == ACT_SOFTPLUS) v = softplus_t<T>(v);
       else if (act == ACT_RELU) v = fmaxf(v, 0.f);
       y[i] = ok ? v : 0.f;
@@ -158,10 +178,13 @@ struct EpiStoreF32 {
   float* out; int ldo;
   RowMeta meta;
   int mask_rows;
+  __device__ __forceinline__ RowState prep(int row) const { return RowState{!mask_rows || meta.valid(row), 1.f}; }
+  __device__ __forceinline__ const float* colvec() const { return nullptr; }
   template <int W>
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W]) const {
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
+                                             const float*) const {
     float y[W];
-    const bool ok = !mask_rows || meta.valid(row);
+    const bool ok = rs.ok;
 #pragma unroll
     for (int i = 0; i < W; ++i) y[i] = ok ? acc[i] : 0.f;
     Act<float>::stv<W>(out + (size_t)row * ldo + col0, y);
@@ -175,9 +198,12 @@ struct EpiInvConv {
   float* zmid; float* zout; T* z0;  // zout / z0 may be null
   int c_off, h, zld;                // active block starts at c_off; z0 = [c_off, c_off + h)
   RowMeta meta;
+  __device__ __forceinline__ RowState prep(int row) const { return RowState{meta.valid(row), 1.f}; }
+  __device__ __forceinline__ const float* colvec() const { return nullptr; }
   template <int W>
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W]) const {
-    const bool ok = meta.valid(row);
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
+                                             const float*) const {
+    const bool ok = rs.ok;
 #pragma unroll
     for (int i = 0; i < W; ++i) {
       const int c = col0 + i;
@@ -206,15 +232,18 @@ struct EpiCoupling {
   int inverse;
   int scaling;            // 0 tanh, 1 exp, 2 sigmoid, 3 translate (reference common.py:775-787)
   RowMeta meta;
+  __device__ __forceinline__ RowState prep(int row) const { return RowState{meta.valid(row), 1.f}; }
+  __device__ __forceinline__ const float* colvec() const { return bias; }
   template <int W>
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W]) const {
-    const bool ok = meta.valid(row);
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
+                                             const float* cv) const {
+    const bool ok = rs.ok;
 #pragma unroll
     for (int i = 0; i < W; i += 2) {
       const int c = (col0 + i) >> 1;
       if (c >= h) continue;
-      const float x = acc[i] + bias[col0 + i];
-      const float b = acc[i + 1] + bias[col0 + i + 1];
+      const float x = acc[i] + cv[i];
+      const float b = acc[i + 1] + cv[i + 1];
       const size_t zi = (size_t)row * zld + c_off + h + c;
       float outv = 0.f, ls = 0.f;
       if (ok) {
@@ -244,9 +273,12 @@ struct EpiEndDgrad {
   T* gu;                  // [n_layers][rows_alloc][n_ch]
   int n_layers, n_ch, rows_alloc;
   RowMeta meta;
+  __device__ __forceinline__ RowState prep(int row) const { return RowState{meta.valid(row), 1.f}; }
+  __device__ __forceinline__ const float* colvec() const { return nullptr; }
   template <int W>
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W]) const {
-    const bool ok = meta.valid(row);
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
+                                             const float*) const {
+    const bool ok = rs.ok;
     for (int l = 0; l < n_layers; ++l) {
       float rv[W], y[W];
       Act<T>::template ldv<W>(r + (size_t)row * ldr + l * n_ch + col0, rv);
@@ -265,14 +297,22 @@ struct EpiDgradAct {
   T* out; int ldo;
   RowMeta meta;
   int act, partial, log2d, ksize;
+  __device__ __forceinline__ RowState prep(int row) const {
+    RowState rs;
+    rs.ok = meta.valid(row);
+    rs.rt = (partial && rs.ok) ? meta.ratio(row, log2d, ksize) : 1.f;
+    return rs;
+  }
+  __device__ __forceinline__ const float* colvec() const { return nullptr; }
   template <int W>
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W]) const {
-    const bool ok = meta.valid(row);
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
+                                             const float*) const {
+    const bool ok = rs.ok;
     float y[W];
     if (ok) {
       float xv[W];
       if (act == ACT_SOFTPLUS) Act<T>::template ldv<W>(x + (size_t)row * ldx + col0, xv);
-      const float rt = partial ? meta.ratio(row, log2d, ksize) : 1.f;
+      const float rt = rs.rt;
 #pragma unroll
       for (int i = 0; i < W; ++i) y[i] = acc[i] * (act == ACT_SOFTPLUS ? softplus_grad_t<T>(xv[i]) : 1.f) * rt;
     } else {
@@ -290,9 +330,12 @@ struct EpiStartDgrad {
   float* g_zmid; int c_off, h, zld;
   int accumulate;
   RowMeta meta;
+  __device__ __forceinline__ RowState prep(int row) const { return RowState{meta.valid(row), 1.f}; }
+  __device__ __forceinline__ const float* colvec() const { return nullptr; }
   template <int W>
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W]) const {
-    const bool ok = meta.valid(row);
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
+                                             const float*) const {
+    const bool ok = rs.ok;
     if (col0 + W <= ctx_ld) {
       float y[W];
       float* dst = g_ctx + (size_t)row * ctx_ld + col0;
@@ -408,10 +451,14 @@ __global__ void __launch_bounds__(kSimtThreads) rowgemm_simt(GemmDesc d, Epi epi
   }
   const int col0 = n0 + tx * 8;
   if (col0 < d.N) {
+    const float* cv = epi.colvec();
+    float cvr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cvr[j] = cv ? cv[col0 + j] : 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int row = row0 + ty * 8 + i;
-      epi.template operator()<8>(row, col0, acc[i]);  // rows past the packed range are gap rows (zeros)
+      const int row = row0 + ty * 8 + i;  // rows past the packed range are gap rows (functors write zeros)
+      epi.template operator()<8>(row, col0, acc[i], epi.prep(row), cvr);
     }
   }
 }

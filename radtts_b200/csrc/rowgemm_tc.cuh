@@ -23,7 +23,8 @@ namespace rb {
 constexpr int kTcBM = 128, kTcBK = 64, kTcMaxBN = 256, kTcStages = 4, kTcThreads = 192;
 constexpr int kTcABytes = kTcBM * kTcBK * 2;       // 16 KB
 constexpr int kTcBBytes = kTcMaxBN * kTcBK * 2;    // 32 KB
-constexpr int kTcSmemBytes = kTcStages * (kTcABytes + kTcBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kTcSmemBytes = kTcStages * (kTcABytes + kTcBBytes) + 1024 /*align slack*/ + 256 /*barriers*/ +
+                             2 * kTcMaxBN * 4 /*per-tile column vector (bias), double buffered*/;
 constexpr int kTcMaxMaps = 4;
 
 struct TcSeg {
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
   uint64_t* tfull = bars + 2 * kTcStages;   // [2]
   uint64_t* tempty = tfull + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* cvec_s = reinterpret_cast<float*>(smem + kTcStages * (kTcABytes + kTcBBytes) + 256);  // [2][kTcMaxBN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_used = p.plan ? p.plan[0] : p.rows_alloc;
@@ -201,6 +203,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
       const int tm = tile % n_tiles_m, tn = tile / n_tiles_m;
       const int row = tm * kTcBM + quad * 32 + lane;
       const int n0 = tn * p.bn;
+      // per-tile staging, off the TMEM critical path: row state in registers, column vector (bias) in smem
+      const RowState rs = epi.prep(row);
+      float* cv = cvec_s + acc * kTcMaxBN;
+      {
+        const float* gv = epi.colvec();
+        const int et = threadIdx.x - 64;  // 0..127 among the epilogue warps
+        for (int i = et; i < p.bn; i += 128) cv[i] = (gv && n0 + i < p.N) ? gv[n0 + i] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * kTcMaxBN + ((uint32_t)(quad * 32) << 16);
@@ -222,7 +233,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(src[q][i]);
-            epi.template operator()<16>(row, n0 + c, v);
+            epi.template operator()<16>(row, n0 + c, v, rs, cv + c);
           }
         }
       };
