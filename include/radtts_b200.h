@@ -237,6 +237,24 @@ RADTTS_API int radtts_affine_apply(const float* z, const float* params, int B, i
 /* y[b,:,t] = W x[b,:,t] for a small dense W (C <= 16): the plain Invertible1x1Conv of BGAP (common.py:431-472). */
 RADTTS_API int radtts_pointwise_conv_small(const float* x, const float* w, int B, int C, int T, float* y, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Persistent bidirectional LSTM recurrence (context BiLSTM, reference radtts.py:284-293, and the text
+ * encoder BiLSTM, common.py:359-371 -- a packed-sequence cuDNN call in the reference).  One cooperative kernel per
+ * pass runs the whole time loop; the x-projection GEMM and the weight-gradient GEMMs stay outside (plain GEMMs).
+ *   gx (2, T, B, 4H) float32: W_ih x_t + b_ih + b_hh per direction (gate order i, f, g, o); whh (2, 4H, H);
+ *   lens (B) int32; h_all (T, B, 2H) out, zeros for t >= lens[b] (packed-sequence semantics);
+ *   gates_save (2, T, B, 4H), c_save (2, T, B, H): activations saved for backward (NULL for inference);
+ *   backward: dh_all (T, B, 2H) -> dgates_all (2, T, B, 4H) (pre-activation gate gradients).
+ *   B <= 32, H <= 592.  ws: radtts_lstm_workspace_bytes(B, H).
+ * ---------------------------------------------------------------------------------------------- */
+RADTTS_API size_t radtts_lstm_workspace_bytes(int B, int H);
+RADTTS_API int radtts_lstm_forward(const float* gx, const float* whh, const int* lens, int T, int B, int H,
+                                   float* h_all, float* gates_save, float* c_save, void* ws, size_t ws_bytes,
+                                   void* stream);
+RADTTS_API int radtts_lstm_backward(const float* dh_all, const float* whh, const int* lens, const float* gates_save,
+                                    const float* c_save, int T, int B, int H, float* dgates_all, void* ws,
+                                    size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

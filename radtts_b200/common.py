@@ -13,7 +13,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
-from . import ops
+from . import lstm_ops, ops
 
 
 def update_params(config, params):
@@ -207,6 +207,17 @@ class ConvLSTMLinear(nn.Module):
         return context
 
 
+def run_bilstm(lstm, x, lens):
+    """pad_packed(lstm(pack_padded(x, lens))) for a batch-first BiLSTM: the persistent CUDA recurrence when the shape
+    fits (csrc/lstm.cu), otherwise the cuDNN packed-sequence path the reference uses."""
+    if lstm_ops.supported(lstm, x):
+        return lstm_ops.bilstm(lstm, x, lens)
+    packed = nn.utils.rnn.pack_padded_sequence(x, lens.long().cpu(), batch_first=True, enforce_sorted=False)
+    lstm.flatten_parameters()
+    out, _ = nn.utils.rnn.pad_packed_sequence(lstm(packed)[0], batch_first=True, total_length=x.shape[1])
+    return out
+
+
 class Encoder(nn.Module):
     """Text encoder: 3 x (partial conv k5 + InstanceNorm + ReLU + dropout) + BiLSTM (reference
     common.py:305-384); outside the hot path, kept as PyTorch / cuDNN."""
@@ -254,9 +265,7 @@ class Encoder(nn.Module):
                 x = self._convs_masked(x, in_lens).transpose(1, 2)
             else:
                 x = self._convs(x).transpose(1, 2)
-            packed = nn.utils.rnn.pack_padded_sequence(x, in_lens.int().cpu(), batch_first=True)
-            self.lstm.flatten_parameters()
-            out, _ = nn.utils.rnn.pad_packed_sequence(self.lstm(packed)[0], batch_first=True)
+            out = run_bilstm(self.lstm, x, in_lens)
         return out
 
     def infer(self, x):

@@ -1,0 +1,322 @@
+// Persistent bidirectional LSTM recurrence ("next" row f-2 of SURVEY section 8: the context BiLSTM of
+// RADTTS.preprocess_context, reference radtts.py:262-302, and the text-encoder BiLSTM, common.py:359-371).
+//
+// cuDNN runs a variable-length (packed) LSTM as ~10 tiny kernels per time step: at T' = 400 that is >4000 launches
+// and ~20 ms per train step -- more than the whole decoder flow stack.  Here the time loop lives inside ONE
+// cooperative kernel per pass: the input projection W_ih x_t (+ biases) for all t is a plain GEMM done beforehand;
+// each CTA owns a slice of U hidden units of one direction, keeps its rows of W_hh resident in shared memory for
+// the whole sequence, and the CTAs of a direction exchange h_t through L2 with one grid barrier per step.
+// Variable lengths follow packed-sequence semantics: state and output are zero for t >= len[b], so the reverse
+// direction starts each utterance at its own last frame.
+//
+// fp32 throughout (state, weights, accumulation).  Gate order i, f, g, o as in torch.nn.LSTM.
+#include "common.cuh"
+
+namespace rb {
+
+constexpr int kLstmThreads = 256;   // 32 batch lanes x 8 slices
+constexpr int kLstmMaxB = 32;
+constexpr int kLstmLd = 33;          // padded smem stride of the transposed [k][batch] staging buffers (bank-conflict free)
+
+struct LstmDims {
+  int T, B, H, U, G;   // U units per CTA, G CTAs per direction (G * U >= H)
+};
+
+__device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ void dir_barrier(unsigned* counter, unsigned nblocks, unsigned& phase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned target = (phase + 1) * nblocks;
+    atomicAdd(counter, 1u);
+    unsigned spins = 0;
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= target) break;
+      if (++spins > (1u << 28)) __trap();
+    }
+    __threadfence();
+  }
+  ++phase;
+  __syncthreads();
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// forward:  gates = gx[t] + W_hh h_{t-1};  c = f c + i g;  h = o tanh(c)
+//   gx     [2][T][B][4H]   x-projection + b_ih + b_hh per direction
+//   whh    [2][4H][H]
+//   h_all  [T][B][2H]      output (direction d in columns [dH, (d+1)H)), zeros for t >= len
+//   gates_save [2][T][B][4H] (i, f, g, o after the non-linearities), c_save [2][T][B][H]   (training only)
+//   hbuf   [2][2][B][H]    ping-pong exchange buffer, zero-initialised;  counters [2] zero-initialised
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLstmThreads, 1)
+lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, const int* __restrict__ lens, LstmDims d,
+                float* __restrict__ h_all, float* __restrict__ gates_save, float* __restrict__ c_save,
+                float* __restrict__ hbuf, unsigned* __restrict__ counters) {
+  extern __shared__ float sm[];
+  const int T = d.T, B = d.B, H = d.H, U = d.U;
+  const int dir = blockIdx.x / d.G, cta = blockIdx.x % d.G;
+  const int u0 = cta * U;
+  const int R = 4 * U;                       // gate rows owned by this CTA
+  float* ws = sm;                            // [H][R]   (k-major, rows contiguous)
+  float* hs = ws + (size_t)H * R;            // [H][32]  h_{t-1} transposed
+  float* red = hs + (size_t)H * kLstmLd;     // [8 slices][R][32]
+  const int tid = threadIdx.x;
+  const int b = tid & 31, slice = tid >> 5;  // 8 k-slices
+  const float* W = whh + (size_t)dir * 4 * H * H;
+  for (int i = tid; i < H * R; i += kLstmThreads) {
+    const int k = i / R, r = i % R;          // r = gate * U + ul
+    const int gate = r / U, ul = r % U;
+    const int u = u0 + ul;
+    ws[i] = u < H ? W[(size_t)(gate * H + u) * H + k] : 0.f;
+  }
+  // state owned by thread (ul = slice' ..): after the reduction thread `tid` finalises unit ul = tid / 32, batch b
+  float c_state = 0.f;
+  const int ul_own = tid >> 5;               // U <= 8 so that U * 32 <= 256 threads own (unit, batch) pairs
+  const int len_b = b < B ? lens[b] : 0;
+  unsigned phase = 0;
+  const int kchunk = (H + 7) / 8;
+  __syncthreads();
+
+  for (int s = 0; s < T; ++s) {
+    const int t = dir == 0 ? s : T - 1 - s;
+    const float* hprev = hbuf + ((size_t)(dir * 2 + (s & 1)) * B) * H;
+    float* hnext = hbuf + ((size_t)(dir * 2 + ((s + 1) & 1)) * B) * H;
+    // stage h_{t-1} (B x H, L2-coherent loads) transposed into smem
+    for (int i = tid; i < kLstmMaxB * H; i += kLstmThreads) {
+      const int bb = i / H, k = i % H;
+      hs[k * kLstmLd + bb] = bb < B ? ldcg(hprev + (size_t)bb * H + k) : 0.f;
+    }
+    __syncthreads();
+    // partial dot products: thread (b, slice) covers k in [slice*kchunk, ...) for all R rows
+    {
+      float acc[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) acc[r] = 0.f;
+      const int k0 = slice * kchunk, k1 = min(k0 + kchunk, H);
+      for (int k = k0; k < k1; ++k) {
+        const float hv = hs[k * kLstmLd + b];
+        const float4* wr = reinterpret_cast<const float4*>(ws + (size_t)k * R);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q * 4 < R) {
+            const float4 w4 = wr[q];
+            acc[q * 4 + 0] = fmaf(w4.x, hv, acc[q * 4 + 0]);
+            acc[q * 4 + 1] = fmaf(w4.y, hv, acc[q * 4 + 1]);
+            acc[q * 4 + 2] = fmaf(w4.z, hv, acc[q * 4 + 2]);
+            acc[q * 4 + 3] = fmaf(w4.w, hv, acc[q * 4 + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (r < R) red[((size_t)slice * R + r) * kLstmMaxB + b] = acc[r];
+    }
+    __syncthreads();
+    // finalise (unit ul_own, batch b)
+    if (ul_own < U) {
+      const int u = u0 + ul_own;
+      float hval = 0.f;
+      if (u < H && b < B) {
+        float g4[4];
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate) {
+          float v = gx[(((size_t)dir * T + t) * B + b) * 4 * H + gate * H + u];
+          const int r = gate * U + ul_own;
+#pragma unroll
+          for (int sl = 0; sl < 8; ++sl) v += red[((size_t)sl * R + r) * kLstmMaxB + b];
+          g4[gate] = v;
+        }
+        const bool on = t < len_b;
+        const float ig = sigmoidf_(g4[0]), fg = sigmoidf_(g4[1]), gg = tanhf(g4[2]), og = sigmoidf_(g4[3]);
+        const float cn = on ? fg * c_state + ig * gg : 0.f;
+        hval = on ? og * tanhf(cn) : 0.f;
+        c_state = cn;
+        if (gates_save) {
+          float* gs = gates_save + (((size_t)dir * T + t) * B + b) * 4 * H;
+          gs[u] = ig; gs[H + u] = fg; gs[2 * H + u] = gg; gs[3 * H + u] = og;
+          c_save[(((size_t)dir * T + t) * B + b) * H + u] = cn;
+        }
+        h_all[((size_t)t * B + b) * 2 * H + dir * H + u] = hval;
+        hnext[(size_t)b * H + u] = hval;
+      }
+    }
+    dir_barrier(counters + dir, d.G, phase);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// backward:  walks time in the opposite order of the forward pass of that direction.
+//   dh_all [T][B][2H] upstream gradient;  dgates_all [2][T][B][4H] out (pre-activation gate gradients)
+//   whh [2][4H][H];  dgbuf [2][2][B][4H] ping-pong exchange of dgates_t (zero-initialised)
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLstmThreads, 1)
+lstm_bwd_kernel(const float* __restrict__ dh_all, const float* __restrict__ whh, const int* __restrict__ lens,
+                const float* __restrict__ gates_save, const float* __restrict__ c_save, LstmDims d,
+                float* __restrict__ dgates_all, float* __restrict__ dgbuf, unsigned* __restrict__ counters) {
+  extern __shared__ float sm[];
+  const int T = d.T, B = d.B, H = d.H, U = d.U;
+  const int dir = blockIdx.x / d.G, cta = blockIdx.x % d.G;
+  const int u0 = cta * U;
+  const int J = 4 * H;
+  float* wt = sm;                              // [J][U]   W_hh^T slice: wt[j][ul] = W[j][u0 + ul]
+  float* dgs = wt + (size_t)J * 8;             // [JC][32] chunk of dgates_{next} transposed
+  const int JC = 512;
+  float* red = dgs + (size_t)JC * kLstmLd;     // [8 slices][8 units][32]
+  const int tid = threadIdx.x;
+  const int b = tid & 31, slice = tid >> 5;
+  const float* W = whh + (size_t)dir * 4 * H * H;
+  for (int i = tid; i < J * 8; i += kLstmThreads) {
+    const int j = i / 8, ul = i % 8;
+    const int u = u0 + ul;
+    wt[i] = (ul < U && u < H) ? W[(size_t)j * H + u] : 0.f;
+  }
+  const int ul_own = tid >> 5;
+  const int len_b = b < B ? lens[b] : 0;
+  float dc_state = 0.f;                        // dL/dc carried to the previous step, for (ul_own, b)
+  unsigned phase = 0;
+  __syncthreads();
+
+  for (int s = 0; s < T; ++s) {
+    // forward of this direction visited t_fwd(s') = dir ? T-1-s' : s'; backward visits them in reverse
+    const int sf = T - 1 - s;
+    const int t = dir == 0 ? sf : T - 1 - sf;
+    const int t_prev = dir == 0 ? t - 1 : t + 1;   // the step whose c feeds this one (c_{t-1} in forward order)
+    const float* dgnext = dgbuf + ((size_t)(dir * 2 + (s & 1)) * B) * J;
+    float* dgcur = dgbuf + ((size_t)(dir * 2 + ((s + 1) & 1)) * B) * J;
+    // dh_rec[b][u] = sum_j dgates_next[b][j] W[j][u]
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int j0 = 0; j0 < J; j0 += JC) {
+      const int jn = min(JC, J - j0);
+      __syncthreads();
+      for (int i = tid; i < kLstmMaxB * jn; i += kLstmThreads) {
+        const int bb = i / jn, jj = i % jn;
+        dgs[jj * kLstmLd + bb] = bb < B ? ldcg(dgnext + (size_t)bb * J + j0 + jj) : 0.f;
+      }
+      __syncthreads();
+      const int jc = (jn + 7) / 8;
+      const int ja = slice * jc, jb = min(ja + jc, jn);
+      for (int jj = ja; jj < jb; ++jj) {
+        const float g = dgs[jj * kLstmLd + b];
+        const float4* wr = reinterpret_cast<const float4*>(wt + (size_t)(j0 + jj) * 8);
+        const float4 w0 = wr[0], w1 = wr[1];
+        acc[0] = fmaf(w0.x, g, acc[0]); acc[1] = fmaf(w0.y, g, acc[1]);
+        acc[2] = fmaf(w0.z, g, acc[2]); acc[3] = fmaf(w0.w, g, acc[3]);
+        acc[4] = fmaf(w1.x, g, acc[4]); acc[5] = fmaf(w1.y, g, acc[5]);
+        acc[6] = fmaf(w1.z, g, acc[6]); acc[7] = fmaf(w1.w, g, acc[7]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[((size_t)slice * 8 + i) * kLstmMaxB + b] = acc[i];
+    __syncthreads();
+    if (ul_own < U) {
+      const int u = u0 + ul_own;
+      if (u < H && b < B) {
+        float dh = dh_all[((size_t)t * B + b) * 2 * H + dir * H + u];
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) dh += red[((size_t)sl * 8 + ul_own) * kLstmMaxB + b];
+        const bool on = t < len_b;
+        float di = 0.f, df = 0.f, dg = 0.f, dout = 0.f;
+        if (on) {
+          const float* gs = gates_save + (((size_t)dir * T + t) * B + b) * 4 * H;
+          const float ig = gs[u], fg = gs[H + u], gg = gs[2 * H + u], og = gs[3 * H + u];
+          const float cn = c_save[(((size_t)dir * T + t) * B + b) * H + u];
+          const bool has_prev = (t_prev >= 0 && t_prev < T) && (t_prev < len_b);
+          const float cp = has_prev ? c_save[(((size_t)dir * T + t_prev) * B + b) * H + u] : 0.f;
+          const float tc = tanhf(cn);
+          const float dc = dh * og * (1.f - tc * tc) + dc_state;
+          dout = dh * tc * og * (1.f - og);
+          di = dc * gg * ig * (1.f - ig);
+          df = dc * cp * fg * (1.f - fg);
+          dg = dc * ig * (1.f - gg * gg);
+          dc_state = dc * fg;
+        } else {
+          dc_state = 0.f;
+        }
+        float* go = dgates_all + (((size_t)dir * T + t) * B + b) * J;
+        go[u] = di; go[H + u] = df; go[2 * H + u] = dg; go[3 * H + u] = dout;
+        float* gc = dgcur + (size_t)b * J;
+        gc[u] = di; gc[H + u] = df; gc[2 * H + u] = dg; gc[3 * H + u] = dout;
+      }
+    }
+    dir_barrier(counters + dir, d.G, phase);
+  }
+}
+
+static int lstm_plan(int H, LstmDims* d) {
+  // U <= 8 units per CTA, at most 74 CTAs per direction (both directions co-resident on 148 SMs)
+  int U = (H + 73) / 74;
+  if (U < 1) U = 1;
+  if (U > 8) return RADTTS_ERR_UNSUPPORTED;
+  d->U = U;
+  d->G = (H + U - 1) / U;
+  return 0;
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" size_t radtts_lstm_workspace_bytes(int B, int H) {
+  // hbuf [2][2][B][H] + dgbuf [2][2][B][4H] + counters
+  return ((size_t)4 * B * H + (size_t)16 * B * H) * sizeof(float) + 256;
+}
+
+extern "C" int radtts_lstm_forward(const float* gx, const float* whh, const int* lens, int T, int B, int H,
+                                   float* h_all, float* gates_save, float* c_save, void* ws, size_t ws_bytes,
+                                   void* stream) {
+  if (!gx || !whh || !lens || !h_all || !ws || T <= 0 || B <= 0 || H <= 0) return RADTTS_ERR_INVALID_ARG;
+  if (B > kLstmMaxB) return RADTTS_ERR_UNSUPPORTED;
+  if (ws_bytes < radtts_lstm_workspace_bytes(B, H)) return RADTTS_ERR_WORKSPACE;
+  LstmDims d{T, B, H, 0, 0};
+  RB_TRY(lstm_plan(H, &d));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* hbuf = reinterpret_cast<float*>(ws);
+  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * B * H * sizeof(float));
+  RB_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)4 * B * H * sizeof(float), st));
+  RB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
+  const int R = 4 * d.U;
+  const size_t smem = ((size_t)H * R + (size_t)H * kLstmLd + (size_t)8 * R * kLstmMaxB) * sizeof(float);
+  if (smem > (size_t)kSmemBudget) return RADTTS_ERR_UNSUPPORTED;
+  static size_t configured = 0;
+  if (smem > configured) {
+    RB_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  void* args[] = {(void*)&gx, (void*)&whh, (void*)&lens, (void*)&d, (void*)&h_all, (void*)&gates_save, (void*)&c_save,
+                  (void*)&hbuf, (void*)&counters};
+  RB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_fwd_kernel, dim3(2 * d.G), dim3(kLstmThreads), args, smem, st));
+  return after_launch();
+}
+
+extern "C" int radtts_lstm_backward(const float* dh_all, const float* whh, const int* lens, const float* gates_save,
+                                    const float* c_save, int T, int B, int H, float* dgates_all, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  if (!dh_all || !whh || !lens || !gates_save || !c_save || !dgates_all || !ws || T <= 0 || B <= 0 || H <= 0)
+    return RADTTS_ERR_INVALID_ARG;
+  if (B > kLstmMaxB) return RADTTS_ERR_UNSUPPORTED;
+  if (ws_bytes < radtts_lstm_workspace_bytes(B, H)) return RADTTS_ERR_WORKSPACE;
+  LstmDims d{T, B, H, 0, 0};
+  RB_TRY(lstm_plan(H, &d));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dgbuf = reinterpret_cast<float*>(ws) + (size_t)4 * B * H;
+  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * B * H * sizeof(float));
+  RB_CUDA(cudaMemsetAsync(dgbuf, 0, (size_t)16 * B * H * sizeof(float), st));
+  RB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
+  const size_t smem = ((size_t)4 * H * 8 + (size_t)512 * kLstmLd + (size_t)8 * 8 * kLstmMaxB) * sizeof(float);
+  if (smem > (size_t)kSmemBudget) return RADTTS_ERR_UNSUPPORTED;
+  static size_t configured = 0;
+  if (smem > configured) {
+    RB_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  void* args[] = {(void*)&dh_all, (void*)&whh, (void*)&lens, (void*)&gates_save, (void*)&c_save, (void*)&d,
+                  (void*)&dgates_all, (void*)&dgbuf, (void*)&counters};
+  RB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_bwd_kernel, dim3(2 * d.G), dim3(kLstmThreads), args, smem, st));
+  return after_launch();
+}

@@ -1,0 +1,89 @@
+"""Bidirectional LSTM over variable-length sequences through the persistent CUDA recurrence (csrc/lstm.cu).
+
+Drop-in for `pad_packed_sequence(lstm(pack_padded_sequence(x, lens)))` on an nn.LSTM(num_layers=1,
+bidirectional=True, batch_first=True) module (reference radtts.py:284-293, common.py:359-371): same parameters
+(including the spectral-norm re-parameterisation hooks), same zero outputs beyond each length, same gradients."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+MAX_B = 32
+MAX_H = 592
+
+
+def supported(lstm, x):
+    return (x.is_cuda and isinstance(lstm, torch.nn.LSTM) and lstm.bidirectional and lstm.num_layers == 1
+            and x.shape[0] <= MAX_B and lstm.hidden_size <= MAX_H and lstm.proj_size == 0)
+
+
+def _effective_weights(lstm):
+    """Runs the module's forward pre-hooks (old-style spectral / weight norm recompute weight_hh_l0*) and returns
+    stacked (w_ih (2,4H,In), w_hh (2,4H,H), bias (2,4H)) with autograd links to the underlying parameters."""
+    for hook in lstm._forward_pre_hooks.values():
+        hook(lstm, ())
+    w_ih = torch.stack((lstm.weight_ih_l0, lstm.weight_ih_l0_reverse))
+    w_hh = torch.stack((lstm.weight_hh_l0, lstm.weight_hh_l0_reverse))
+    bias = torch.stack((lstm.bias_ih_l0 + lstm.bias_hh_l0, lstm.bias_ih_l0_reverse + lstm.bias_hh_l0_reverse))
+    return w_ih, w_hh, bias
+
+
+class _BiLSTMFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_tm, lens, w_ih, w_hh, bias):
+        T, B, _ = x_tm.shape
+        H = w_hh.shape[2]
+        dev = x_tm.device
+        need_bwd = any(ctx.needs_input_grad)
+        # input projection for every step: one GEMM per direction (plain library GEMM; autocast-aware)
+        gx = (torch.matmul(x_tm.reshape(1, T * B, -1), w_ih.transpose(1, 2)).float()
+              + bias.float()[:, None, :]).reshape(2, T, B, 4 * H).contiguous()
+        whh = w_hh.detach().float().contiguous()
+        h_all = torch.empty((T, B, 2 * H), dtype=torch.float32, device=dev)
+        gates = torch.empty((2, T, B, 4 * H), dtype=torch.float32, device=dev) if need_bwd else None
+        cs = torch.empty((2, T, B, H), dtype=torch.float32, device=dev) if need_bwd else None
+        L = _lib.lib()
+        nws = int(L.radtts_lstm_workspace_bytes(B, H))
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        _lib.check(L.radtts_lstm_forward(_lib.ptr(gx), _lib.ptr(whh), _lib.ptr(lens), T, B, H, _lib.ptr(h_all),
+                                         _lib.ptr(gates), _lib.ptr(cs), _lib.ptr(ws), ctypes.c_size_t(nws),
+                                         _lib.stream_of(x_tm)), "radtts_lstm_forward")
+        if need_bwd:
+            ctx.save_for_backward(x_tm, lens, w_ih, whh, gates, cs, h_all)
+        return h_all
+
+    @staticmethod
+    def backward(ctx, dh_all):
+        x_tm, lens, w_ih, whh, gates, cs, h_all = ctx.saved_tensors
+        T, B, _ = x_tm.shape
+        H = whh.shape[2]
+        dev = x_tm.device
+        dh_all = dh_all.float().contiguous()
+        dg = torch.empty((2, T, B, 4 * H), dtype=torch.float32, device=dev)
+        L = _lib.lib()
+        nws = int(L.radtts_lstm_workspace_bytes(B, H))
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        _lib.check(L.radtts_lstm_backward(_lib.ptr(dh_all), _lib.ptr(whh), _lib.ptr(lens), _lib.ptr(gates), _lib.ptr(cs),
+                                          T, B, H, _lib.ptr(dg), _lib.ptr(ws), ctypes.c_size_t(nws),
+                                          _lib.stream_of(x_tm)), "radtts_lstm_backward")
+        dg2 = dg.reshape(2, T * B, 4 * H)
+        xf = x_tm.reshape(T * B, -1).float()
+        d_x = torch.matmul(dg2, w_ih.float()).sum(0).reshape(x_tm.shape).to(x_tm.dtype)
+        d_w_ih = torch.matmul(dg2.transpose(1, 2), xf)
+        # h_{t-1} in each direction's own time order
+        zeros = torch.zeros((1, B, H), dtype=torch.float32, device=dev)
+        h_prev_f = torch.cat((zeros, h_all[:-1, :, :H]), 0).reshape(T * B, H)
+        h_prev_r = torch.cat((h_all[1:, :, H:], zeros), 0).reshape(T * B, H)
+        d_w_hh = torch.stack((dg2[0].t() @ h_prev_f, dg2[1].t() @ h_prev_r))
+        d_bias = dg2.sum(1)
+        return d_x, None, d_w_ih.to(w_ih.dtype), d_w_hh, d_bias
+
+
+def bilstm(lstm, x, lens):
+    """x (B, T, In) batch-first, lens (B,) -> (B, T, 2H) with zeros beyond each length."""
+    w_ih, w_hh, bias = _effective_weights(lstm)
+    lens32 = lens.to(device=x.device, dtype=torch.int32).contiguous()
+    x_tm = x.transpose(0, 1).contiguous()
+    h = _BiLSTMFn.apply(x_tm, lens32, w_ih, w_hh, bias)
+    return h.transpose(0, 1)

@@ -10,7 +10,8 @@ from torch import nn
 from . import alignment, ops
 from .attribute_prediction_model import get_attribute_prediction_model
 from .common import (AffineTransformationLayer, ConvAttention, Encoder, ExponentialClass, Invertible1x1Conv,
-                     Invertible1x1ConvLUS, LengthRegulator, LinearNorm, _apply_lstm_norm, get_mask_from_lengths)
+                     Invertible1x1ConvLUS, LengthRegulator, LinearNorm, _apply_lstm_norm, get_mask_from_lengths,
+                     run_bilstm)
 
 
 class FlowStep(nn.Module):
@@ -177,12 +178,7 @@ class RADTTS(nn.Module):
         if self.use_context_lstm:
             if self.context_lstm_w_f0_and_energy and extras:
                 ctx = torch.cat([ctx] + extras, 1)
-            lens = (out_lens // g).long().cpu()
-            packed = nn.utils.rnn.pack_padded_sequence(ctx.transpose(1, 2), lens, batch_first=True,
-                                                       enforce_sorted=False)
-            self.context_lstm.flatten_parameters()
-            out, _ = nn.utils.rnn.pad_packed_sequence(self.context_lstm(packed)[0], batch_first=True)
-            ctx = out.transpose(1, 2)
+            ctx = run_bilstm(self.context_lstm, ctx.transpose(1, 2), out_lens // g).transpose(1, 2)
         if not self.context_lstm_w_f0_and_energy and extras:
             ctx = torch.cat([ctx] + extras, 1)
         return ctx

@@ -1,0 +1,47 @@
+"""Persistent BiLSTM kernel (csrc/lstm.cu) vs the cuDNN packed-sequence path the reference uses
+(radtts.py:284-293): outputs and every gradient, with spectral norm on the recurrent weights."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from radtts_b200 import lstm_ops
+from radtts_b200.common import _apply_lstm_norm
+
+pytestmark = pytest.mark.gpu
+
+
+def _cudnn_path(lstm, x, lens):
+    packed = nn.utils.rnn.pack_padded_sequence(x, lens.cpu(), batch_first=True, enforce_sorted=False)
+    out, _ = nn.utils.rnn.pad_packed_sequence(lstm(packed)[0], batch_first=True, total_length=x.shape[1])
+    return out
+
+
+@pytest.mark.parametrize("In,H,B,T", [(64, 40, 5, 23), (1040, 520, 8, 61), (512, 256, 32, 37)])
+def test_bilstm_matches_cudnn(cuda_lib, In, H, B, T):
+    torch.manual_seed(0)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        lstm = _apply_lstm_norm(nn.LSTM(In, H, 1, batch_first=True, bidirectional=True), "spectral").cuda().eval()
+        x = (torch.randn(B, T, In, device="cuda") * 0.5).requires_grad_(True)
+        lens = torch.randint(max(1, T // 3), T + 1, (B,), device="cuda")
+        lens[0] = T
+        w = torch.randn(B, T, 2 * H, device="cuda")
+        assert lstm_ops.supported(lstm, x)
+        y = lstm_ops.bilstm(lstm, x, lens)
+        (y * w).sum().backward()
+        got = {n: p.grad.clone() for n, p in lstm.named_parameters()}
+        gx = x.grad.clone()
+        lstm.zero_grad()
+        x.grad = None
+        y_ref = _cudnn_path(lstm.train(), x, lens)   # cuDNN RNN backward needs train mode
+        (y_ref * w).sum().backward()
+        assert torch.allclose(y, y_ref, rtol=1e-4, atol=2e-5), float((y - y_ref).abs().max())
+        assert torch.allclose(gx, x.grad, rtol=1e-3, atol=1e-4), float((gx - x.grad).abs().max())
+        for n, p in lstm.named_parameters():
+            ref = p.grad
+            err = float((got[n] - ref).norm() / (ref.norm() + 1e-12))
+            assert err < 2e-3, (n, err)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
