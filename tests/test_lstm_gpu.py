@@ -23,7 +23,9 @@ def test_bilstm_matches_cudnn(cuda_lib, In, H, B, T):
     tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
-        lstm = _apply_lstm_norm(nn.LSTM(In, H, 1, batch_first=True, bidirectional=True), "spectral").cuda().eval()
+        # plain weights here: an old-style spectral-norm hook power-iterates (and mutates u, v) on every train-mode
+        # call, so two calls never see the same effective weights; the spectral case is checked forward-only below
+        lstm = nn.LSTM(In, H, 1, batch_first=True, bidirectional=True).cuda()
         x = (torch.randn(B, T, In, device="cuda") * 0.5).requires_grad_(True)
         lens = torch.randint(max(1, T // 3), T + 1, (B,), device="cuda")
         lens[0] = T
@@ -35,7 +37,7 @@ def test_bilstm_matches_cudnn(cuda_lib, In, H, B, T):
         gx = x.grad.clone()
         lstm.zero_grad()
         x.grad = None
-        y_ref = _cudnn_path(lstm.train(), x, lens)   # cuDNN RNN backward needs train mode
+        y_ref = _cudnn_path(lstm, x, lens)
         (y_ref * w).sum().backward()
         assert torch.allclose(y, y_ref, rtol=1e-4, atol=2e-5), float((y - y_ref).abs().max())
         assert torch.allclose(gx, x.grad, rtol=1e-3, atol=1e-4), float((gx - x.grad).abs().max())
@@ -43,5 +45,25 @@ def test_bilstm_matches_cudnn(cuda_lib, In, H, B, T):
             ref = p.grad
             err = float((got[n] - ref).norm() / (ref.norm() + 1e-12))
             assert err < 2e-3, (n, err)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+
+
+def test_bilstm_spectral_norm_eval_forward(cuda_lib):
+    torch.manual_seed(1)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        lstm = _apply_lstm_norm(nn.LSTM(96, 72, 1, batch_first=True, bidirectional=True), "spectral").cuda()
+        x = torch.randn(6, 29, 96, device="cuda") * 0.5
+        lens = torch.tensor([29, 11, 20, 29, 5, 17], device="cuda")
+        with torch.no_grad():
+            lstm.train()
+            for _ in range(5):            # let the power iteration settle, then freeze it
+                _cudnn_path(lstm, x, lens)
+            lstm.eval()
+            y = lstm_ops.bilstm(lstm, x, lens)
+            y_ref = _cudnn_path(lstm, x, lens)
+        assert torch.allclose(y, y_ref, rtol=1e-4, atol=2e-5), float((y - y_ref).abs().max())
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
