@@ -11,12 +11,14 @@
 //
 // fp32 throughout (state, weights, accumulation).  Gate order i, f, g, o as in torch.nn.LSTM.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace rb {
 
 constexpr int kLstmThreads = 256;   // 32 batch lanes x 8 slices
 constexpr int kLstmMaxB = 32;
-constexpr int kLstmLd = 33;          // padded smem stride of the transposed [k][batch] staging buffers (bank-conflict free)
+constexpr int kLstmLd = 32;          // exchange buffers are stored transposed ([k][32 batch lanes]) in GLOBAL memory, so one
+                                    // 1-D bulk async copy (TMA) per step lands them in smem in the conflict-free layout
 
 struct LstmDims {
   int T, B, H, U, G;   // U units per CTA, G CTAs per direction (G * U >= H)
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, const int* __restrict__ lens, LstmDims d,
                 float* __restrict__ h_all, float* __restrict__ gates_save, float* __restrict__ c_save,
                 float* __restrict__ hbuf, unsigned* __restrict__ counters) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(128) float sm[];
   const int T = d.T, B = d.B, H = d.H, U = d.U;
   const int dir = blockIdx.x / d.G, cta = blockIdx.x % d.G;
   const int u0 = cta * U;
@@ -64,7 +66,9 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
   float* ws = sm;                            // [H][R]   (k-major, rows contiguous)
   float* hs = ws + (size_t)H * R;            // [H][32]  h_{t-1} transposed
   float* red = hs + (size_t)H * kLstmLd;     // [8 slices][R][32]
+  __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   const int b = tid & 31, slice = tid >> 5;  // 8 k-slices
   const float* W = whh + (size_t)dir * 4 * H * H;
   for (int i = tid; i < H * R; i += kLstmThreads) {
@@ -83,14 +87,23 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
 
   for (int s = 0; s < T; ++s) {
     const int t = dir == 0 ? s : T - 1 - s;
-    const float* hprev = hbuf + ((size_t)(dir * 2 + (s & 1)) * B) * H;
-    float* hnext = hbuf + ((size_t)(dir * 2 + ((s + 1) & 1)) * B) * H;
-    // stage h_{t-1} (B x H, L2-coherent loads) transposed into smem
-    for (int i = tid; i < kLstmMaxB * H; i += kLstmThreads) {
-      const int bb = i / H, k = i % H;
-      hs[k * kLstmLd + bb] = bb < B ? ldcg(hprev + (size_t)bb * H + k) : 0.f;
+    const float* hprev = hbuf + ((size_t)(dir * 2 + (s & 1)) * kLstmMaxB) * H;   // [H][32]
+    float* hnext = hbuf + ((size_t)(dir * 2 + ((s + 1) & 1)) * kLstmMaxB) * H;
+    // stage h_{t-1}: one bulk async copy of the whole [H][32] exchange block (written by the other CTAs of this
+    // direction before the barrier; the proxy fence orders the async-proxy read after those generic-proxy writes)
+    if (tid == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      mbar_arrive_expect_tx(&bar, (uint32_t)(H * kLstmMaxB * sizeof(float)));
+      bulk_g2s(hs, hprev, (uint32_t)(H * kLstmMaxB * sizeof(float)), &bar);
     }
-    __syncthreads();
+    // x-projection of this step for the (unit, batch) this thread finalises: issued before the wait
+    float gxv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ul_own < U && u0 + ul_own < H && b < B) {
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate)
+        gxv[gate] = gx[(((size_t)dir * T + t) * B + b) * 4 * H + gate * H + u0 + ul_own];
+    }
+    mbar_wait(&bar, (uint32_t)(s & 1));
     // partial dot products: thread (b, slice) covers k in [slice*kchunk, ...) for all R rows
     {
       float acc[32];
@@ -124,7 +137,7 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
         float g4[4];
 #pragma unroll
         for (int gate = 0; gate < 4; ++gate) {
-          float v = gx[(((size_t)dir * T + t) * B + b) * 4 * H + gate * H + u];
+          float v = gxv[gate];
           const int r = gate * U + ul_own;
 #pragma unroll
           for (int sl = 0; sl < 8; ++sl) v += red[((size_t)sl * R + r) * kLstmMaxB + b];
@@ -141,7 +154,8 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
           c_save[(((size_t)dir * T + t) * B + b) * H + u] = cn;
         }
         h_all[((size_t)t * B + b) * 2 * H + dir * H + u] = hval;
-        hnext[(size_t)b * H + u] = hval;
+        hnext[(size_t)u * kLstmMaxB + b] = hval;
+        asm volatile("fence.proxy.async;" ::: "memory");   // these stores are consumed by other CTAs' bulk copies
       }
     }
     dir_barrier(counters + dir, d.G, phase);
@@ -157,16 +171,19 @@ __global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_bwd_kernel(const float* __restrict__ dh_all, const float* __restrict__ whh, const int* __restrict__ lens,
                 const float* __restrict__ gates_save, const float* __restrict__ c_save, LstmDims d,
                 float* __restrict__ dgates_all, float* __restrict__ dgbuf, unsigned* __restrict__ counters) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(128) float sm[];
   const int T = d.T, B = d.B, H = d.H, U = d.U;
   const int dir = blockIdx.x / d.G, cta = blockIdx.x % d.G;
   const int u0 = cta * U;
   const int J = 4 * H;
   float* wt = sm;                              // [J][U]   W_hh^T slice: wt[j][ul] = W[j][u0 + ul]
-  float* dgs = wt + (size_t)J * 8;             // [JC][32] chunk of dgates_{next} transposed
-  const int JC = 512;
-  float* red = dgs + (size_t)JC * kLstmLd;     // [8 slices][8 units][32]
+  const int JC = H;                            // one gate block per chunk
+  float* dgs = wt + (size_t)J * 8;             // [2][JC][32] double-buffered chunks of dgates_{next} (transposed)
+  float* red = dgs + (size_t)2 * JC * kLstmLd; // [8 slices][8 units][32]
+  __shared__ __align__(8) uint64_t bar[2];
   const int tid = threadIdx.x;
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+  unsigned nfill = 0;                          // chunk copies issued so far (buffer = nfill & 1, parity = (nfill >> 1) & 1)
   const int b = tid & 31, slice = tid >> 5;
   const float* W = whh + (size_t)dir * 4 * H * H;
   for (int i = tid; i < J * 8; i += kLstmThreads) {
@@ -185,24 +202,46 @@ lstm_bwd_kernel(const float* __restrict__ dh_all, const float* __restrict__ whh,
     const int sf = T - 1 - s;
     const int t = dir == 0 ? sf : T - 1 - sf;
     const int t_prev = dir == 0 ? t - 1 : t + 1;   // the step whose c feeds this one (c_{t-1} in forward order)
-    const float* dgnext = dgbuf + ((size_t)(dir * 2 + (s & 1)) * B) * J;
-    float* dgcur = dgbuf + ((size_t)(dir * 2 + ((s + 1) & 1)) * B) * J;
+    const float* dgnext = dgbuf + ((size_t)(dir * 2 + (s & 1)) * kLstmMaxB) * J;   // [J][32]
+    float* dgcur = dgbuf + ((size_t)(dir * 2 + ((s + 1) & 1)) * kLstmMaxB) * J;
+    const uint32_t chunk_bytes = (uint32_t)(JC * kLstmMaxB * sizeof(float));
+    auto issue = [&](int chunk) {
+      const unsigned buf = nfill & 1u;
+      mbar_arrive_expect_tx(&bar[buf], chunk_bytes);
+      bulk_g2s(dgs + (size_t)buf * JC * kLstmLd, dgnext + (size_t)chunk * JC * kLstmMaxB, chunk_bytes, &bar[buf]);
+    };
+    if (tid == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      issue(0);
+    }
+    // operands of the element-wise part, fetched while the copies are in flight
+    const bool mine = ul_own < U && u0 + ul_own < H && b < B;
+    const bool on = mine && t < len_b;
+    float dh = 0.f, ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cn = 0.f, cp = 0.f;
+    if (mine) dh = dh_all[((size_t)t * B + b) * 2 * H + dir * H + u0 + ul_own];
+    if (on) {
+      const int u = u0 + ul_own;
+      const float* gs = gates_save + (((size_t)dir * T + t) * B + b) * 4 * H;
+      ig = gs[u]; fg = gs[H + u]; gg = gs[2 * H + u]; og = gs[3 * H + u];
+      cn = c_save[(((size_t)dir * T + t) * B + b) * H + u];
+      const bool has_prev = (t_prev >= 0 && t_prev < T) && (t_prev < len_b);
+      cp = has_prev ? c_save[(((size_t)dir * T + t_prev) * B + b) * H + u] : 0.f;
+    }
     // dh_rec[b][u] = sum_j dgates_next[b][j] W[j][u]
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int j0 = 0; j0 < J; j0 += JC) {
-      const int jn = min(JC, J - j0);
-      __syncthreads();
-      for (int i = tid; i < kLstmMaxB * jn; i += kLstmThreads) {
-        const int bb = i / jn, jj = i % jn;
-        dgs[jj * kLstmLd + bb] = bb < B ? ldcg(dgnext + (size_t)bb * J + j0 + jj) : 0.f;
-      }
-      __syncthreads();
-      const int jc = (jn + 7) / 8;
-      const int ja = slice * jc, jb = min(ja + jc, jn);
+    for (int chunk = 0; chunk < 4; ++chunk) {
+      const unsigned buf = nfill & 1u, par = (nfill >> 1) & 1u;
+      ++nfill;
+      if (tid == 0 && chunk + 1 < 4) issue(chunk + 1);   // the other buffer was released by the sync of chunk - 1
+      mbar_wait(&bar[buf], par);
+      const float* dg_s = dgs + (size_t)buf * JC * kLstmLd;
+      const int j0 = chunk * JC;
+      const int jc = (JC + 7) / 8;
+      const int ja = slice * jc, jb = min(ja + jc, JC);
       for (int jj = ja; jj < jb; ++jj) {
-        const float g = dgs[jj * kLstmLd + b];
+        const float g = dg_s[jj * kLstmLd + b];
         const float4* wr = reinterpret_cast<const float4*>(wt + (size_t)(j0 + jj) * 8);
         const float4 w0 = wr[0], w1 = wr[1];
         acc[0] = fmaf(w0.x, g, acc[0]); acc[1] = fmaf(w0.y, g, acc[1]);
@@ -210,39 +249,34 @@ lstm_bwd_kernel(const float* __restrict__ dh_all, const float* __restrict__ whh,
         acc[4] = fmaf(w1.x, g, acc[4]); acc[5] = fmaf(w1.y, g, acc[5]);
         acc[6] = fmaf(w1.z, g, acc[6]); acc[7] = fmaf(w1.w, g, acc[7]);
       }
+      __syncthreads();   // everyone is done with this buffer before it is refilled two chunks later
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[((size_t)slice * 8 + i) * kLstmMaxB + b] = acc[i];
     __syncthreads();
-    if (ul_own < U) {
+    if (mine) {
       const int u = u0 + ul_own;
-      if (u < H && b < B) {
-        float dh = dh_all[((size_t)t * B + b) * 2 * H + dir * H + u];
 #pragma unroll
-        for (int sl = 0; sl < 8; ++sl) dh += red[((size_t)sl * 8 + ul_own) * kLstmMaxB + b];
-        const bool on = t < len_b;
-        float di = 0.f, df = 0.f, dg = 0.f, dout = 0.f;
-        if (on) {
-          const float* gs = gates_save + (((size_t)dir * T + t) * B + b) * 4 * H;
-          const float ig = gs[u], fg = gs[H + u], gg = gs[2 * H + u], og = gs[3 * H + u];
-          const float cn = c_save[(((size_t)dir * T + t) * B + b) * H + u];
-          const bool has_prev = (t_prev >= 0 && t_prev < T) && (t_prev < len_b);
-          const float cp = has_prev ? c_save[(((size_t)dir * T + t_prev) * B + b) * H + u] : 0.f;
-          const float tc = tanhf(cn);
-          const float dc = dh * og * (1.f - tc * tc) + dc_state;
-          dout = dh * tc * og * (1.f - og);
-          di = dc * gg * ig * (1.f - ig);
-          df = dc * cp * fg * (1.f - fg);
-          dg = dc * ig * (1.f - gg * gg);
-          dc_state = dc * fg;
-        } else {
-          dc_state = 0.f;
-        }
-        float* go = dgates_all + (((size_t)dir * T + t) * B + b) * J;
-        go[u] = di; go[H + u] = df; go[2 * H + u] = dg; go[3 * H + u] = dout;
-        float* gc = dgcur + (size_t)b * J;
-        gc[u] = di; gc[H + u] = df; gc[2 * H + u] = dg; gc[3 * H + u] = dout;
+      for (int sl = 0; sl < 8; ++sl) dh += red[((size_t)sl * 8 + ul_own) * kLstmMaxB + b];
+      float di = 0.f, df = 0.f, dg = 0.f, dout = 0.f;
+      if (on) {
+        const float tc = tanhf(cn);
+        const float dc = dh * og * (1.f - tc * tc) + dc_state;
+        dout = dh * tc * og * (1.f - og);
+        di = dc * gg * ig * (1.f - ig);
+        df = dc * cp * fg * (1.f - fg);
+        dg = dc * ig * (1.f - gg * gg);
+        dc_state = dc * fg;
+      } else {
+        dc_state = 0.f;
       }
+      float* go = dgates_all + (((size_t)dir * T + t) * B + b) * J;
+      go[u] = di; go[H + u] = df; go[2 * H + u] = dg; go[3 * H + u] = dout;
+      dgcur[(size_t)u * kLstmMaxB + b] = di;
+      dgcur[(size_t)(H + u) * kLstmMaxB + b] = df;
+      dgcur[(size_t)(2 * H + u) * kLstmMaxB + b] = dg;
+      dgcur[(size_t)(3 * H + u) * kLstmMaxB + b] = dout;
+      asm volatile("fence.proxy.async;" ::: "memory");
     }
     dir_barrier(counters + dir, d.G, phase);
   }
@@ -263,8 +297,9 @@ static int lstm_plan(int H, LstmDims* d) {
 using namespace rb;
 
 extern "C" size_t radtts_lstm_workspace_bytes(int B, int H) {
-  // hbuf [2][2][B][H] + dgbuf [2][2][B][4H] + counters
-  return ((size_t)4 * B * H + (size_t)16 * B * H) * sizeof(float) + 256;
+  // hbuf [2][2][H][32] + dgbuf [2][2][4H][32] + counters (exchange buffers are padded to 32 batch lanes)
+  (void)B;
+  return ((size_t)4 * 32 * H + (size_t)16 * 32 * H) * sizeof(float) + 256;
 }
 
 extern "C" int radtts_lstm_forward(const float* gx, const float* whh, const int* lens, int T, int B, int H,
@@ -277,8 +312,8 @@ extern "C" int radtts_lstm_forward(const float* gx, const float* whh, const int*
   RB_TRY(lstm_plan(H, &d));
   cudaStream_t st = (cudaStream_t)stream;
   float* hbuf = reinterpret_cast<float*>(ws);
-  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * B * H * sizeof(float));
-  RB_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)4 * B * H * sizeof(float), st));
+  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * 32 * H * sizeof(float));
+  RB_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)4 * 32 * H * sizeof(float), st));
   RB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
   const int R = 4 * d.U;
   const size_t smem = ((size_t)H * R + (size_t)H * kLstmLd + (size_t)8 * R * kLstmMaxB) * sizeof(float);
@@ -304,11 +339,11 @@ extern "C" int radtts_lstm_backward(const float* dh_all, const float* whh, const
   LstmDims d{T, B, H, 0, 0};
   RB_TRY(lstm_plan(H, &d));
   cudaStream_t st = (cudaStream_t)stream;
-  float* dgbuf = reinterpret_cast<float*>(ws) + (size_t)4 * B * H;
-  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * B * H * sizeof(float));
-  RB_CUDA(cudaMemsetAsync(dgbuf, 0, (size_t)16 * B * H * sizeof(float), st));
+  float* dgbuf = reinterpret_cast<float*>(ws) + (size_t)4 * 32 * H;
+  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * 32 * H * sizeof(float));
+  RB_CUDA(cudaMemsetAsync(dgbuf, 0, (size_t)16 * 32 * H * sizeof(float), st));
   RB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
-  const size_t smem = ((size_t)4 * H * 8 + (size_t)512 * kLstmLd + (size_t)8 * 8 * kLstmMaxB) * sizeof(float);
+  const size_t smem = ((size_t)4 * H * 8 + (size_t)2 * H * kLstmLd + (size_t)8 * 8 * kLstmMaxB) * sizeof(float);
   if (smem > (size_t)kSmemBudget) return RADTTS_ERR_UNSUPPORTED;
   static size_t configured = 0;
   if (smem > configured) {
