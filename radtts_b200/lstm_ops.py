@@ -51,6 +51,7 @@ class _BiLSTMFn(torch.autograd.Function):
                                          _lib.stream_of(x_tm)), "radtts_lstm_forward")
         if need_bwd:
             ctx.save_for_backward(x_tm, lens, w_ih, whh, gates, cs, h_all)
+            ctx.low_prec = torch.is_autocast_enabled()   # the weight / input gradient GEMMs follow the forward's precision
         return h_all
 
     @staticmethod
@@ -67,15 +68,17 @@ class _BiLSTMFn(torch.autograd.Function):
         _lib.check(L.radtts_lstm_backward(_lib.ptr(dh_all), _lib.ptr(whh), _lib.ptr(lens), _lib.ptr(gates), _lib.ptr(cs),
                                           T, B, H, _lib.ptr(dg), _lib.ptr(ws), ctypes.c_size_t(nws),
                                           _lib.stream_of(x_tm)), "radtts_lstm_backward")
+        mm = torch.bfloat16 if ctx.low_prec else torch.float32   # plain library GEMMs; bf16 under autocast
         dg2 = dg.reshape(2, T * B, 4 * H)
-        xf = x_tm.reshape(T * B, -1).float()
-        d_x = torch.matmul(dg2, w_ih.float()).sum(0).reshape(x_tm.shape).to(x_tm.dtype)
-        d_w_ih = torch.matmul(dg2.transpose(1, 2), xf)
+        dgm = dg2.to(mm)
+        xf = x_tm.reshape(T * B, -1).to(mm)
+        d_x = torch.matmul(dgm, w_ih.to(mm)).float().sum(0).reshape(x_tm.shape).to(x_tm.dtype)
+        d_w_ih = torch.matmul(dgm.transpose(1, 2), xf).float()
         # h_{t-1} in each direction's own time order
         zeros = torch.zeros((1, B, H), dtype=torch.float32, device=dev)
-        h_prev_f = torch.cat((zeros, h_all[:-1, :, :H]), 0).reshape(T * B, H)
-        h_prev_r = torch.cat((h_all[1:, :, H:], zeros), 0).reshape(T * B, H)
-        d_w_hh = torch.stack((dg2[0].t() @ h_prev_f, dg2[1].t() @ h_prev_r))
+        h_prev_f = torch.cat((zeros, h_all[:-1, :, :H]), 0).reshape(T * B, H).to(mm)
+        h_prev_r = torch.cat((h_all[1:, :, H:], zeros), 0).reshape(T * B, H).to(mm)
+        d_w_hh = torch.stack((dgm[0].t() @ h_prev_f, dgm[1].t() @ h_prev_r)).float()
         d_bias = dg2.sum(1)
         return d_x, None, d_w_ih.to(w_ih.dtype), d_w_hh, d_bias
 
