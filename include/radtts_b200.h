@@ -255,6 +255,19 @@ RADTTS_API int radtts_lstm_backward(const float* dh_all, const float* whh, const
                                     const float* c_save, int T, int B, int H, float* dgates_all, void* ws,
                                     size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Attention CTC loss, fused.  Replaces AttentionCTCLoss.forward (reference loss.py:118-135): blank
+ * logit + per-utterance log-softmax + nn.CTCLoss(zero_infinity=True) against targets 1..K_b, and its backward.
+ *   attn_logprob (B,1,T1,T2) float32 logits; in_lens / out_lens (B) int64 device; T2 <= 511.
+ *   losses (B) out: -log p(target) per utterance (0 when infinite); the reference's scalar is mean_b(losses[b]/K_b).
+ *   grad (B,1,T1,T2) out: d(mean_b(losses[b]/K_b)) / d attn_logprob, fully written.
+ *   ws: radtts_attn_ctc_workspace_bytes (alpha lattice).
+ * ---------------------------------------------------------------------------------------------- */
+RADTTS_API size_t radtts_attn_ctc_workspace_bytes(int B, int T1, int T2);
+RADTTS_API int radtts_attn_ctc(const float* attn_logprob, const int64_t* in_lens, const int64_t* out_lens, int B, int T1,
+                               int T2, float blank_logprob, float* losses, float* grad, void* ws, size_t ws_bytes,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

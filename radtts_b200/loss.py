@@ -78,6 +78,14 @@ class AttentionCTCLoss(nn.Module):
 
     def forward(self, attn_logprob, in_lens, out_lens):
         B, _, T1, T2 = attn_logprob.shape
+        if attn_logprob.is_cuda and 2 * T2 + 1 <= 1024:
+            from . import ops
+            return ops.attention_ctc_loss(attn_logprob, in_lens, out_lens, self.blank_logprob)
+        return self.forward_torch(attn_logprob, in_lens, out_lens)
+
+    def forward_torch(self, attn_logprob, in_lens, out_lens):
+        """Batched PyTorch formulation (CPU tensors, or text longer than the fused kernel supports)."""
+        B, _, T1, T2 = attn_logprob.shape
         lp = F.pad(attn_logprob[:, 0], (1, 0), value=self.blank_logprob)                 # (B, T1, T2+1)
         cls = torch.arange(T2 + 1, device=lp.device)[None, None, :]
         # classes beyond key_len are excluded from the softmax; a large finite negative (exp underflows to exactly 0)

@@ -633,3 +633,34 @@ def conv_attention(att, queries, keys, mask, key_lens, attn_prior):
     if mask is None:
         key_lens = None
     return _ConvAttnFn.apply(q_enc, k_enc, attn_prior, key_lens, 0.0005)
+
+
+class _AttnCTCFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, attn_logprob, in_lens, out_lens, blank_logprob):
+        x = attn_logprob.float().contiguous()
+        B, _, T1, T2 = x.shape
+        dev = x.device
+        il = in_lens.to(device=dev, dtype=torch.int64).contiguous()
+        ol = out_lens.to(device=dev, dtype=torch.int64).contiguous()
+        losses = torch.empty(B, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(x)
+        L = _lib.lib()
+        nws = int(L.radtts_attn_ctc_workspace_bytes(B, T1, T2))
+        ws = _lib.workspace(dev, nws)
+        _lib.check(L.radtts_attn_ctc(_lib.ptr(x), _lib.ptr(il), _lib.ptr(ol), B, T1, T2, ctypes.c_float(blank_logprob),
+                                     _lib.ptr(losses), _lib.ptr(grad), _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
+                                     _lib.stream_of(x)), "radtts_attn_ctc")
+        ctx.save_for_backward(grad)
+        return (losses / il.clamp(min=1).to(losses.dtype)).mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None
+
+
+def attention_ctc_loss(attn_logprob, in_lens, out_lens, blank_logprob=-1.0):
+    """AttentionCTCLoss.forward (reference loss.py:118-135) as one fused CUDA launch, no host synchronisation."""
+    _lib.require_cuda(attn_logprob)
+    return _AttnCTCFn.apply(attn_logprob, in_lens, out_lens, float(blank_logprob))

@@ -124,3 +124,23 @@ def test_decoder_config_forward_matches_reference(golden_dir, cuda_lib):
     for i in (0, 7):
         assert torch.allclose(_valid(out["log_s_list"][i], lens).cpu(),
                               _valid(torch.from_numpy(g["log_s_%d" % i]), lens.cpu()), rtol=1e-3, atol=1e-5)
+
+
+def test_fused_attention_ctc_matches_torch(cuda_lib):
+    """Fused CTC kernel vs the batched PyTorch formulation (itself checked against the reference's
+    per-utterance loop on CPU): value and gradient."""
+    torch.manual_seed(3)
+    for (B, T1, T2) in [(4, 50, 17), (3, 120, 40), (2, 33, 33)]:
+        lp = (torch.randn(B, 1, T1, T2, device="cuda") * 2 - 3)
+        in_lens = torch.randint(max(1, T2 // 2), T2 + 1, (B,), device="cuda")
+        out_lens = torch.randint(T2, T1 + 1, (B,), device="cuda")
+        in_lens[0], out_lens[0] = T2, T1
+        crit = rloss.AttentionCTCLoss()
+        a = lp.clone().requires_grad_(True)
+        la = crit(a, in_lens, out_lens)
+        (ga,) = torch.autograd.grad(la * 1.7, a)
+        r = lp.clone().requires_grad_(True)
+        lr = crit.forward_torch(r, in_lens, out_lens)
+        (gr,) = torch.autograd.grad(lr * 1.7, r)
+        assert abs(float(la) - float(lr)) < 1e-4 * abs(float(lr)) + 1e-6, (float(la), float(lr))
+        assert torch.allclose(ga, gr, rtol=1e-3, atol=1e-6), float((ga - gr).abs().max())
