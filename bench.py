@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--t1", type=int, default=800)
     ap.add_argument("--t2", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -233,9 +234,20 @@ def main():
     peaks = load_peaks()
 
     model = make_model(device).train()
-    ts = TrainStep(model, configs.LOSS_WEIGHTS, bf16=True, ddp=world > 1, device_ids=[local] if world > 1 else None)
+    use_graph = (world == 1) and not args.no_graph
+    ts = TrainStep(model, configs.LOSS_WEIGHTS, bf16=True, ddp=world > 1, device_ids=[local] if world > 1 else None,
+                   capturable=use_graph)
     host_batches = [pinned_batch(args.batch, args.t1, args.t2, seed=1000 + 17 * rank + i) for i in range(2)]
     dev_batches = [to_device(b, device) for b in host_batches]
+    graph_note = "eager"
+    if use_graph:
+        try:
+            ts.capture(dev_batches[0])
+            graph_note = "cuda_graph"
+        except Exception as e:  # fall back to the eager step, say so in the JSON line
+            graph_note = "eager (graph capture failed: %s)" % str(e).splitlines()[0][:120]
+            torch.cuda.synchronize()
+            ts = TrainStep(model, configs.LOSS_WEIGHTS, bf16=True)
     frames_per_step_local = float(sum(int(b["out_lens"].sum()) for b in host_batches)) / len(host_batches)
     h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
 
@@ -248,7 +260,8 @@ def main():
     losses = []
 
     def step_e2e():
-        b = to_device(host_batches[it["i"] % len(host_batches)], device)
+        hb = host_batches[it["i"] % len(host_batches)]
+        b = hb if ts.graph is not None else to_device(hb, device)   # graph mode copies host -> static device buffers
         loss = ts.step(b)
         losses.append(float(loss.item()))   # device -> host read of the step's result
         it["i"] += 1
@@ -299,6 +312,7 @@ def main():
                 "gpu_launches": int(launches * world), "clocks": clocks, "roofline": roofline, "cpu_baseline": cb,
                 "loss_last": losses[-1] if losses else None}
         line["config"]["global_batch"] = args.batch * world
+        line["config"]["execution"] = graph_note
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

@@ -8,7 +8,7 @@ from . import loss as rloss
 
 class TrainStep:
     def __init__(self, model, loss_weights, lr=1e-4, weight_decay=1e-6, grad_clip_val=1.0, bf16=True,
-                 binarize_attention=True, use_binarization_loss=True, ddp=False, device_ids=None):
+                 binarize_attention=True, use_binarization_loss=True, ddp=False, device_ids=None, capturable=False):
         self.raw_model = model
         self.model = model
         if ddp:
@@ -22,7 +22,12 @@ class TrainStep:
         self.use_bin_loss = use_binarization_loss
         self.grad_clip_val = grad_clip_val
         params = [p for p in model.parameters() if p.requires_grad]
-        self.optimizer = torch.optim.RAdam(params, lr=lr, weight_decay=weight_decay, foreach=True)
+        self.capturable = bool(capturable)
+        self.optimizer = torch.optim.RAdam(params, lr=lr, weight_decay=weight_decay, foreach=True,
+                                           capturable=self.capturable)
+        self.graph = None
+        self.static_batch = None
+        self.static_loss = None
 
     def forward_loss(self, batch):
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.bf16):
@@ -39,7 +44,33 @@ class TrainStep:
                 total = total + self.bin_loss(out["attn"], out["attn_soft"]) * self.loss_weights["binarization_loss_weight"]
         return total, out
 
+    def capture(self, example_batch, warmup=3):
+        """Captures the whole step (forward, losses, backward, clip, RAdam) into one CUDA graph.  Possible because the
+        step has no host synchronisation left (device-side frame plans, fused CTC, persistent LSTM); requires a fixed
+        batch shape -- lengths stay device data and may change from replay to replay."""
+        assert self.capturable, "construct TrainStep(capturable=True) to use CUDA graphs"
+        self.static_batch = {k: v.clone() for k, v in example_batch.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager_step(self.static_batch)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.static_loss = self._eager_step(self.static_batch)
+        self.graph = graph
+
     def step(self, batch):
+        if self.graph is not None:
+            for k, v in batch.items():
+                self.static_batch[k].copy_(v, non_blocking=True)
+            self.graph.replay()
+            return self.static_loss
+        return self._eager_step(batch)
+
+    def _eager_step(self, batch):
         self.optimizer.zero_grad(set_to_none=True)
         total, _ = self.forward_loss(batch)
         total.backward()
