@@ -276,6 +276,8 @@ def main():
     ms = time_region(step_resident, args.steps, world)
     torch.cuda.profiler.stop()
     launches = _lib.launch_count() - launches0
+    if ts.graph is not None:
+        launches = ts.launches_per_replay * args.steps   # replays re-issue the launches recorded at capture time
     clocks = sampler.stop() if sampler else None
     frames_total = sum_over_ranks(frames_per_step_local, world)
     value = frames_total * args.steps / (ms / 1e3)

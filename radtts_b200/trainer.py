@@ -26,6 +26,7 @@ class TrainStep:
         self.optimizer = torch.optim.RAdam(params, lr=lr, weight_decay=weight_decay, foreach=True,
                                            capturable=self.capturable)
         self.graph = None
+        self.launches_per_replay = 0
         self.static_batch = None
         self.static_loss = None
 
@@ -57,9 +58,12 @@ class TrainStep:
                 self._eager_step(self.static_batch)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import _lib
         graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(graph):
             self.static_loss = self._eager_step(self.static_batch)
+        self.launches_per_replay = _lib.launch_count() - n0   # kernels of libradtts_b200.so inside one replay
         self.graph = graph
 
     def step(self, batch):
