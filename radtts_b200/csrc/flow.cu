@@ -3,6 +3,8 @@
 // The contractions run through rowgemm_simt (fp32) or rowgemm_tc (bf16 tcgen05); see rowgemm.cuh.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "flow_common.cuh"
 #include "flow_layout.cuh"
@@ -300,7 +302,7 @@ static int wn_and_coupling(const radtts_flow_dims& d, const uint8_t* base, const
   g.seg[1] = Seg{buf.z0, 128, 0, 0, 128};
   g.w = base + L.w_start; g.ldw = L.ctx_ld + 128; g.N = nc;
   {
-    EpiBiasAct<T> e{x, nc, 0, reinterpret_cast<const float*>(base + L.b_start), meta, ACT_NONE, 0, 0, k, 1};
+    EpiBiasAct<T, ACT_NONE> e{x, nc, 0, reinterpret_cast<const float*>(base + L.b_start), meta, ACT_NONE, 0, 0, k, 1};
     RB_TRY((run_gemm<T>(g, e, st)));
   }
   for (int i = 0; i < nl; ++i) {
@@ -310,15 +312,16 @@ static int wn_and_coupling(const radtts_flow_dims& d, const uint8_t* base, const
     for (int t = 0; t < k; ++t) g.seg[t] = Seg{xi, nc, (t - k / 2) << i, 0, nc};
     g.w = base + L.w_in[i]; g.ldw = k * nc; g.N = nc;
     {
-      EpiBiasAct<T> e{xo, nc, 0, reinterpret_cast<const float*>(base + L.b_in[i]), meta, ACT_SOFTPLUS,
-                      d.partial_padding, i, k, 1};
+      EpiBiasAct<T, ACT_SOFTPLUS> e{xo, nc, 0, reinterpret_cast<const float*>(base + L.b_in[i]), meta, ACT_SOFTPLUS,
+                                    d.partial_padding, i, k, 1};
       RB_TRY((run_gemm<T>(g, e, st)));
     }
     g.nseg = 1;
     g.seg[0] = Seg{xo, nc, 0, 0, nc};
     g.w = base + L.w_rs[i]; g.ldw = nc; g.N = nc;
     {
-      EpiBiasAct<T> e{r, nl * nc, i * nc, reinterpret_cast<const float*>(base + L.b_rs[i]), meta, ACT_SOFTPLUS, 0, 0, k, 1};
+      EpiBiasAct<T, ACT_SOFTPLUS> e{r, nl * nc, i * nc, reinterpret_cast<const float*>(base + L.b_rs[i]), meta, ACT_SOFTPLUS,
+                                    0, 0, k, 1};
       RB_TRY((run_gemm<T>(g, e, st)));
     }
   }
@@ -449,9 +452,12 @@ static int wn_layer_impl(const radtts_flow_dims& d, const uint8_t* base, const P
   g.plan = pv.hdr();
   g.nseg = k;
   for (int t = 0; t < k; ++t) g.seg[t] = Seg{x + (size_t)layer * rows * nc, nc, (t - k / 2) << layer, 0, nc};
+  static const int dbg_nseg = [] { const char* e = getenv("RADTTS_DEBUG_NSEG"); return e ? atoi(e) : 0; }();
+  if (dbg_nseg > 0 && dbg_nseg < k) g.nseg = dbg_nseg;   // profiling experiment: shorter K
   g.w = base + L.w_in[layer]; g.ldw = k * nc; g.N = nc;
-  EpiBiasAct<T> e{x + (size_t)(layer + 1) * rows * nc, nc, 0, reinterpret_cast<const float*>(base + L.b_in[layer]), meta,
-                  ACT_SOFTPLUS, d.partial_padding, layer, k, 1};
+  EpiBiasAct<T, ACT_SOFTPLUS> e{x + (size_t)(layer + 1) * rows * nc, nc, 0,
+                                reinterpret_cast<const float*>(base + L.b_in[layer]), meta, ACT_SOFTPLUS, d.partial_padding,
+                                layer, k, 1};
   return run_gemm<T>(g, e, st);
 }
 extern "C" int radtts_wn_layer_forward(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,

@@ -125,8 +125,8 @@ static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const P
       gd.nseg = 1 + k;
     }
     gd.w = base + L.w_dg[i]; gd.ldw = L.dg_k[i]; gd.N = nc;
-    EpiDgradAct<T> e{x + (size_t)(i + 1) * rows * nc, nc, gv + (size_t)i * rows * nc, nc, meta, ACT_SOFTPLUS,
-                     d.partial_padding, i, k};
+    EpiDgradAct<T, ACT_SOFTPLUS> e{x + (size_t)(i + 1) * rows * nc, nc, gv + (size_t)i * rows * nc, nc, meta, ACT_SOFTPLUS,
+                                   d.partial_padding, i, k};
     RB_TRY((run_gemm<T>(gd, e, st)));
   }
   // 4. g_x0 and start dgrad
@@ -134,7 +134,7 @@ static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const P
   for (int t = 0; t < k; ++t) gd.seg[t] = Seg{gv, nc, -(t - k / 2), 0, nc};
   gd.w = base + L.w_dg0; gd.ldw = k * nc; gd.N = nc;
   {
-    EpiDgradAct<T> e{nullptr, nc, gx0, nc, meta, ACT_NONE, 0, 0, k};
+    EpiDgradAct<T, ACT_NONE> e{nullptr, nc, gx0, nc, meta, ACT_NONE, 0, 0, k};
     RB_TRY((run_gemm<T>(gd, e, st)));
   }
   gd.nseg = 1;

@@ -95,9 +95,8 @@ __device__ __forceinline__ float softplus20(float x) { return x > 20.f ? x : log
 // d softplus / dx expressed through the OUTPUT y = softplus(x):  sigmoid(x) = 1 - exp(-y)
 __device__ __forceinline__ float softplus_grad_from_out(float y) { return 1.f - expf(-y); }
 // bf16 path: MUFU-based versions (their ~1e-6 error is far below the bf16 rounding of the stored result)
-__device__ __forceinline__ float softplus20_fast(float x) {
-  return x > 20.f ? x : fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x)));
-}
+// branch-free: for x > 20 the correction term is below fp32 resolution, so the threshold needs no select
+__device__ __forceinline__ float softplus20_fast(float x) { return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))); }
 __device__ __forceinline__ float softplus_grad_from_out_fast(float y) { return 1.f - __expf(-y); }
 template <typename T>
 __device__ __forceinline__ float softplus_t(float x) { return sizeof(T) == 2 ? softplus20_fast(x) : softplus20(x); }
@@ -132,20 +131,20 @@ struct RowState {
 // epilogue functors:
 //   RowState prep(int row)                                  once per row per tile
 //   const float* colvec()                                   per-column vector (bias) the engine stages per tile, or null
-//   template<int W> void operator()(int row, int col0, const float (&acc)[W], const RowState& rs, const float* cv)
-//        cv[i] = colvec()[col0 + i]  (already offset to the chunk)
+//   template<int W> void operator()(int row, int col0, const float (&acc)[W], const RowState& rs, const float (&cv)[W])
+//        cv[i] = colvec()[col0 + i], handed over in registers (zeros when colvec() is null)
 // `row` < rows in use, col0 % W == 0, col0 + W <= round_up(N, W); functors guard col < N themselves when
 // their N is not a multiple of W.
 // ------------------------------------------------------------------------------------------------------
 enum : int { ACT_NONE = 0, ACT_SOFTPLUS = 1, ACT_RELU = 2 };
 
 // y = act(acc * ratio + bias) on valid rows, 0 on gap rows.            (start / in_layers / res_skip / ReLU convs)
-template <typename T>
+template <typename T, int ACT = -1>   // ACT >= 0: activation fixed at compile time (branch-free inner loop)
 struct EpiBiasAct {
   T* out; int ldo; int col_off;
   const float* bias;
   RowMeta meta;
-  int act;
+  int act;           // used when ACT < 0
   int partial;       // 1: multiply acc by the partial-conv ratio
   int log2d, ksize;
   int mask_rows;     // 1: zero gap rows; 0: plain conv (ConvAttention projections)
@@ -158,15 +157,16 @@ struct EpiBiasAct {
   __device__ __forceinline__ const float* colvec() const { return bias; }
   template <int W>
   __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
-                                             const float* cv) const {
+                                             const float (&cv)[W]) const {
     float y[W];
     const bool ok = rs.ok;
     const float rt = rs.rt;
 #pragma unroll
     for (int i = 0; i < W; ++i) {
       float v = acc[i] * rt + cv[i];
-      if (act == ACT_SOFTPLUS) v = softplus_t<T>(v);
-      else if (act == ACT_RELU) v = fmaxf(v, 0.f);
+      const int a = ACT >= 0 ? ACT : act;
+      if (a == ACT_SOFTPLUS) v = softplus_t<T>(v);
+      else if (a == ACT_RELU) v = fmaxf(v, 0.f);
       y[i] = ok ? v : 0.f;
     }
     Act<T>::template stv<W>(out + (size_t)row * ldo + col_off + col0, y);
@@ -182,7 +182,7 @@ struct EpiStoreF32 {
   __device__ __forceinline__ const float* colvec() const { return nullptr; }
   template <int W>
   __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
-                                             const float*) const {
+                                             const float (&)[W]) const {
     float y[W];
     const bool ok = rs.ok;
 #pragma unroll
@@ -202,7 +202,7 @@ struct EpiInvConv {
   __device__ __forceinline__ const float* colvec() const { return nullptr; }
   template <int W>
   __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
-                                             const float*) const {
+                                             const float (&)[W]) const {
     const bool ok = rs.ok;
 #pragma unroll
     for (int i = 0; i < W; ++i) {
@@ -236,7 +236,7 @@ struct EpiCoupling {
   __device__ __forceinline__ const float* colvec() const { return bias; }
   template <int W>
   __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
-                                             const float* cv) const {
+                                             const float (&cv)[W]) const {
     const bool ok = rs.ok;
 #pragma unroll
     for (int i = 0; i < W; i += 2) {
@@ -277,7 +277,7 @@ struct EpiEndDgrad {
   __device__ __forceinline__ const float* colvec() const { return nullptr; }
   template <int W>
   __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
-                                             const float*) const {
+                                             const float (&)[W]) const {
     const bool ok = rs.ok;
     for (int l = 0; l < n_layers; ++l) {
       float rv[W], y[W];
@@ -291,7 +291,7 @@ struct EpiEndDgrad {
 
 // dgrad through a softplus'ed (partial) conv output x:  g_v = acc * softplus'(x) * ratio   (valid rows)
 // with act == ACT_NONE / partial == 0 it is a plain masked store (g_x0 of `start`).
-template <typename T>
+template <typename T, int ACT = -1>
 struct EpiDgradAct {
   const T* x; int ldx;    // forward OUTPUT of the layer whose pre-activation gradient is produced
   T* out; int ldo;
@@ -306,15 +306,16 @@ struct EpiDgradAct {
   __device__ __forceinline__ const float* colvec() const { return nullptr; }
   template <int W>
   __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
-                                             const float*) const {
+                                             const float (&)[W]) const {
     const bool ok = rs.ok;
     float y[W];
     if (ok) {
       float xv[W];
-      if (act == ACT_SOFTPLUS) Act<T>::template ldv<W>(x + (size_t)row * ldx + col0, xv);
+      const int a = ACT >= 0 ? ACT : act;
+      if (a == ACT_SOFTPLUS) Act<T>::template ldv<W>(x + (size_t)row * ldx + col0, xv);
       const float rt = rs.rt;
 #pragma unroll
-      for (int i = 0; i < W; ++i) y[i] = acc[i] * (act == ACT_SOFTPLUS ? softplus_grad_t<T>(xv[i]) : 1.f) * rt;
+      for (int i = 0; i < W; ++i) y[i] = acc[i] * (a == ACT_SOFTPLUS ? softplus_grad_t<T>(xv[i]) : 1.f) * rt;
     } else {
 #pragma unroll
       for (int i = 0; i < W; ++i) y[i] = 0.f;
@@ -334,7 +335,7 @@ struct EpiStartDgrad {
   __device__ __forceinline__ const float* colvec() const { return nullptr; }
   template <int W>
   __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
-                                             const float*) const {
+                                             const float (&)[W]) const {
     const bool ok = rs.ok;
     if (col0 + W <= ctx_ld) {
       float y[W];

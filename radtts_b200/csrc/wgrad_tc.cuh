@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 5) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     return q;
   };
 
-  if (warp == 0) {
+  if (warp == 4) {   // producer / MMA issuer on the high warp ids (arbiter priority), epilogue on warps 0-3
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
