@@ -27,12 +27,18 @@ struct LstmDims {
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-__device__ __forceinline__ void dir_barrier(unsigned* counter, unsigned nblocks, unsigned& phase) {
+// Split barrier among the CTAs of one direction: arrive right after the exchange stores, do the remaining (bulky,
+// nobody-waits-for-them) stores of the step, then wait.  Keeps those stores off the barrier's critical path.
+__device__ __forceinline__ void dir_barrier_arrive(unsigned* counter) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned target = (phase + 1) * nblocks;
     atomicAdd(counter, 1u);
+  }
+}
+__device__ __forceinline__ void dir_barrier_wait(unsigned* counter, unsigned nblocks, unsigned& phase) {
+  if (threadIdx.x == 0) {
+    const unsigned target = (phase + 1) * nblocks;
     unsigned spins = 0;
     while (true) {
       unsigned v;
@@ -66,9 +72,12 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
   float* ws = sm;                            // [H][R]   (k-major, rows contiguous)
   float* hs = ws + (size_t)H * R;            // [H][32]  h_{t-1} transposed
   float* red = hs + (size_t)H * kLstmLd;     // [8 slices][R][32]
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar[8];   // one per k-slice: a warp starts as soon as ITS slice of h has landed
   const int tid = threadIdx.x;
-  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1);
+    mbar_fence_init();
+  }
   const int b = tid & 31, slice = tid >> 5;  // 8 k-slices
   const float* W = whh + (size_t)dir * 4 * H * H;
   for (int i = tid; i < H * R; i += kLstmThreads) {
@@ -93,8 +102,16 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
     // direction before the barrier; the proxy fence orders the async-proxy read after those generic-proxy writes)
     if (tid == 0) {
       asm volatile("fence.proxy.async;" ::: "memory");
-      mbar_arrive_expect_tx(&bar, (uint32_t)(H * kLstmMaxB * sizeof(float)));
-      bulk_g2s(hs, hprev, (uint32_t)(H * kLstmMaxB * sizeof(float)), &bar);
+      for (int sl = 0; sl < 8; ++sl) {
+        const int ka = sl * kchunk, kb = min(ka + kchunk, H);
+        if (kb > ka) {
+          const uint32_t bytes = (uint32_t)((kb - ka) * kLstmMaxB * sizeof(float));
+          mbar_arrive_expect_tx(&bar[sl], bytes);
+          bulk_g2s(hs + (size_t)ka * kLstmLd, hprev + (size_t)ka * kLstmMaxB, bytes, &bar[sl]);
+        } else {
+          mbar_arrive(&bar[sl]);
+        }
+      }
     }
     // x-projection of this step for the (unit, batch) this thread finalises: issued before the wait
     float gxv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -103,7 +120,7 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
       for (int gate = 0; gate < 4; ++gate)
         gxv[gate] = gx[(((size_t)dir * T + t) * B + b) * 4 * H + gate * H + u0 + ul_own];
     }
-    mbar_wait(&bar, (uint32_t)(s & 1));
+    mbar_wait(&bar[slice], (uint32_t)(s & 1));
     // partial dot products: thread (b, slice) covers k in [slice*kchunk, ...) for all R rows
     {
       float acc[32];
@@ -130,9 +147,10 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
     }
     __syncthreads();
     // finalise (unit ul_own, batch b)
+    bool wrote = false;
+    float hval = 0.f, ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cn = 0.f;
     if (ul_own < U) {
       const int u = u0 + ul_own;
-      float hval = 0.f;
       if (u < H && b < B) {
         float g4[4];
 #pragma unroll
@@ -144,21 +162,26 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
           g4[gate] = v;
         }
         const bool on = t < len_b;
-        const float ig = sigmoidf_(g4[0]), fg = sigmoidf_(g4[1]), gg = tanhf(g4[2]), og = sigmoidf_(g4[3]);
-        const float cn = on ? fg * c_state + ig * gg : 0.f;
+        ig = sigmoidf_(g4[0]); fg = sigmoidf_(g4[1]); gg = tanhf(g4[2]); og = sigmoidf_(g4[3]);
+        cn = on ? fg * c_state + ig * gg : 0.f;
         hval = on ? og * tanhf(cn) : 0.f;
         c_state = cn;
-        if (gates_save) {
-          float* gs = gates_save + (((size_t)dir * T + t) * B + b) * 4 * H;
-          gs[u] = ig; gs[H + u] = fg; gs[2 * H + u] = gg; gs[3 * H + u] = og;
-          c_save[(((size_t)dir * T + t) * B + b) * H + u] = cn;
-        }
-        h_all[((size_t)t * B + b) * 2 * H + dir * H + u] = hval;
-        hnext[(size_t)u * kLstmMaxB + b] = hval;
-        asm volatile("fence.proxy.async;" ::: "memory");   // these stores are consumed by other CTAs' bulk copies
+        hnext[(size_t)u * kLstmMaxB + b] = hval;           // the only store other CTAs wait for
+        asm volatile("fence.proxy.async;" ::: "memory");   // ... and they read it with bulk async copies
+        wrote = true;
       }
     }
-    dir_barrier(counters + dir, d.G, phase);
+    dir_barrier_arrive(counters + dir);
+    if (wrote) {
+      const int u = u0 + ul_own;
+      if (gates_save) {
+        float* gs = gates_save + (((size_t)dir * T + t) * B + b) * 4 * H;
+        gs[u] = ig; gs[H + u] = fg; gs[2 * H + u] = gg; gs[3 * H + u] = og;
+        c_save[(((size_t)dir * T + t) * B + b) * H + u] = cn;
+      }
+      h_all[((size_t)t * B + b) * 2 * H + dir * H + u] = hval;
+    }
+    dir_barrier_wait(counters + dir, d.G, phase);
   }
 }
 
@@ -254,6 +277,7 @@ lstm_bwd_kernel(const float* __restrict__ dh_all, const float* __restrict__ whh,
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[((size_t)slice * 8 + i) * kLstmMaxB + b] = acc[i];
     __syncthreads();
+    float d4[4] = {0.f, 0.f, 0.f, 0.f};
     if (mine) {
       const int u = u0 + ul_own;
 #pragma unroll
@@ -270,15 +294,20 @@ lstm_bwd_kernel(const float* __restrict__ dh_all, const float* __restrict__ whh,
       } else {
         dc_state = 0.f;
       }
-      float* go = dgates_all + (((size_t)dir * T + t) * B + b) * J;
-      go[u] = di; go[H + u] = df; go[2 * H + u] = dg; go[3 * H + u] = dout;
       dgcur[(size_t)u * kLstmMaxB + b] = di;
       dgcur[(size_t)(H + u) * kLstmMaxB + b] = df;
       dgcur[(size_t)(2 * H + u) * kLstmMaxB + b] = dg;
       dgcur[(size_t)(3 * H + u) * kLstmMaxB + b] = dout;
       asm volatile("fence.proxy.async;" ::: "memory");
+      d4[0] = di; d4[1] = df; d4[2] = dg; d4[3] = dout;
     }
-    dir_barrier(counters + dir, d.G, phase);
+    dir_barrier_arrive(counters + dir);
+    if (mine) {
+      const int u = u0 + ul_own;
+      float* go = dgates_all + (((size_t)dir * T + t) * B + b) * J;
+      go[u] = d4[0]; go[H + u] = d4[1]; go[2 * H + u] = d4[2]; go[3 * H + u] = d4[3];
+    }
+    dir_barrier_wait(counters + dir, d.G, phase);
   }
 }
 
