@@ -71,14 +71,19 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
   const int R = 4 * U;                       // gate rows owned by this CTA
   float* ws = sm;                            // [H][R]   (k-major, rows contiguous)
   float* hs = ws + (size_t)H * R;            // [H][32]  h_{t-1} transposed
-  float* red = hs + (size_t)H * kLstmLd;     // [8 slices][R][32]
-  __shared__ __align__(8) uint64_t bar[8];   // one per k-slice: a warp starts as soon as ITS slice of h has landed
+  float* red = hs + (size_t)H * kLstmLd;     // [16 k-slices][R][32]
+  __shared__ __align__(8) uint64_t bar[8];   // one per warp (= 2 k-slices): a warp starts as soon as ITS part of h landed
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1);
     mbar_fence_init();
   }
-  const int b = tid & 31, slice = tid >> 5;  // 8 k-slices
+  const int b = tid & 31;                    // batch lane of the (unit, batch) pair this thread finalises
+  // GEMM mapping: 8 x 8 register tiles (gate rows x batch), 16 tiles cover 32 x 32, 16 k-slices of ~H/16.
+  // smem -> register traffic per FMA drops 4x vs one-row-of-batch per thread, which was the limiter.
+  const int tile = tid & 15, kslice = tid >> 4;
+  const int rt = (tile >> 2) * 8, bt = (tile & 3) * 8;
+  const int warp = tid >> 5;
   const float* W = whh + (size_t)dir * 4 * H * H;
   for (int i = tid; i < H * R; i += kLstmThreads) {
     const int k = i / R, r = i % R;          // r = gate * U + ul
@@ -91,7 +96,7 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
   const int ul_own = tid >> 5;               // U <= 8 so that U * 32 <= 256 threads own (unit, batch) pairs
   const int len_b = b < B ? lens[b] : 0;
   unsigned phase = 0;
-  const int kchunk = (H + 7) / 8;
+  const int kchunk = (H + 15) / 16;          // k-slice length; a warp owns slices 2*warp, 2*warp + 1
   __syncthreads();
 
   for (int s = 0; s < T; ++s) {
@@ -103,7 +108,7 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
     if (tid == 0) {
       asm volatile("fence.proxy.async;" ::: "memory");
       for (int sl = 0; sl < 8; ++sl) {
-        const int ka = sl * kchunk, kb = min(ka + kchunk, H);
+        const int ka = min(2 * sl * kchunk, H), kb = min(ka + 2 * kchunk, H);
         if (kb > ka) {
           const uint32_t bytes = (uint32_t)((kb - ka) * kLstmMaxB * sizeof(float));
           mbar_arrive_expect_tx(&bar[sl], bytes);
@@ -120,30 +125,36 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
       for (int gate = 0; gate < 4; ++gate)
         gxv[gate] = gx[(((size_t)dir * T + t) * B + b) * 4 * H + gate * H + u0 + ul_own];
     }
-    mbar_wait(&bar[slice], (uint32_t)(s & 1));
-    // partial dot products: thread (b, slice) covers k in [slice*kchunk, ...) for all R rows
+    mbar_wait(&bar[warp], (uint32_t)(s & 1));
+    // partial products: thread (tile, kslice) accumulates an 8 x 8 block over its k-slice
     {
-      float acc[32];
+      float acc[8][8];
 #pragma unroll
-      for (int r = 0; r < 32; ++r) acc[r] = 0.f;
-      const int k0 = slice * kchunk, k1 = min(k0 + kchunk, H);
-      for (int k = k0; k < k1; ++k) {
-        const float hv = hs[k * kLstmLd + b];
-        const float4* wr = reinterpret_cast<const float4*>(ws + (size_t)k * R);
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (q * 4 < R) {
-            const float4 w4 = wr[q];
-            acc[q * 4 + 0] = fmaf(w4.x, hv, acc[q * 4 + 0]);
-            acc[q * 4 + 1] = fmaf(w4.y, hv, acc[q * 4 + 1]);
-            acc[q * 4 + 2] = fmaf(w4.z, hv, acc[q * 4 + 2]);
-            acc[q * 4 + 3] = fmaf(w4.w, hv, acc[q * 4 + 3]);
-          }
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+      const int k0 = min(kslice * kchunk, H), k1 = min(k0 + kchunk, H);
+      if (rt < R) {
+        for (int k = k0; k < k1; ++k) {
+          const float4 w0 = *reinterpret_cast<const float4*>(ws + (size_t)k * R + rt);
+          const float4 w1 = *reinterpret_cast<const float4*>(ws + (size_t)k * R + rt + 4);
+          const float4 h0 = *reinterpret_cast<const float4*>(hs + (size_t)k * kLstmLd + bt);
+          const float4 h1 = *reinterpret_cast<const float4*>(hs + (size_t)k * kLstmLd + bt + 4);
+          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(w[i], h[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (rt + i >= R) break;
+          float* rr = red + ((size_t)kslice * R + rt + i) * kLstmMaxB + bt;
+          *reinterpret_cast<float4*>(rr) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+          *reinterpret_cast<float4*>(rr + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
         }
       }
-#pragma unroll
-      for (int r = 0; r < 32; ++r)
-        if (r < R) red[((size_t)slice * R + r) * kLstmMaxB + b] = acc[r];
     }
     __syncthreads();
     // finalise (unit ul_own, batch b)
@@ -158,7 +169,7 @@ lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, con
           float v = gxv[gate];
           const int r = gate * U + ul_own;
 #pragma unroll
-          for (int sl = 0; sl < 8; ++sl) v += red[((size_t)sl * R + r) * kLstmMaxB + b];
+          for (int sl = 0; sl < 16; ++sl) v += red[((size_t)sl * R + r) * kLstmMaxB + b];
           g4[gate] = v;
         }
         const bool on = t < len_b;
@@ -200,14 +211,18 @@ lstm_bwd_kernel(const float* __restrict__ dh_all, const float* __restrict__ whh,
   const int u0 = cta * U;
   const int J = 4 * H;
   float* wt = sm;                              // [J][U]   W_hh^T slice: wt[j][ul] = W[j][u0 + ul]
-  const int JC = H;                            // one gate block per chunk
+  const int JC = H / 2;                        // 8 chunks of dgates_{next} per step (H is even)
+  const int NCHUNK = 8;
   float* dgs = wt + (size_t)J * 8;             // [2][JC][32] double-buffered chunks of dgates_{next} (transposed)
-  float* red = dgs + (size_t)2 * JC * kLstmLd; // [8 slices][8 units][32]
+  float* red = dgs + (size_t)2 * JC * kLstmLd; // [32 j-slices][8 units][32]
   __shared__ __align__(8) uint64_t bar[2];
   const int tid = threadIdx.x;
   if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
   unsigned nfill = 0;                          // chunk copies issued so far (buffer = nfill & 1, parity = (nfill >> 1) & 1)
-  const int b = tid & 31, slice = tid >> 5;
+  const int b = tid & 31;
+  // GEMM mapping: 4 x 8 register tiles (units x batch), 8 tiles cover 8 x 32, 32 j-slices per chunk
+  const int tile = tid & 7, jslice = tid >> 3;
+  const int ut = (tile >> 2) * 4, bt = (tile & 3) * 8;
   const float* W = whh + (size_t)dir * 4 * H * H;
   for (int i = tid; i < J * 8; i += kLstmThreads) {
     const int j = i / 8, ul = i % 8;
@@ -251,37 +266,45 @@ lstm_bwd_kernel(const float* __restrict__ dh_all, const float* __restrict__ whh,
       cp = has_prev ? c_save[(((size_t)dir * T + t_prev) * B + b) * H + u] : 0.f;
     }
     // dh_rec[b][u] = sum_j dgates_next[b][j] W[j][u]
-    float acc[8];
+    float acc[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int chunk = 0; chunk < 4; ++chunk) {
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int chunk = 0; chunk < NCHUNK; ++chunk) {
       const unsigned buf = nfill & 1u, par = (nfill >> 1) & 1u;
       ++nfill;
-      if (tid == 0 && chunk + 1 < 4) issue(chunk + 1);   // the other buffer was released by the sync of chunk - 1
+      if (tid == 0 && chunk + 1 < NCHUNK) issue(chunk + 1);   // the other buffer was released by the sync of chunk - 1
       mbar_wait(&bar[buf], par);
       const float* dg_s = dgs + (size_t)buf * JC * kLstmLd;
       const int j0 = chunk * JC;
-      const int jc = (JC + 7) / 8;
-      const int ja = slice * jc, jb = min(ja + jc, JC);
+      const int jc = (JC + 31) / 32;
+      const int ja = min(jslice * jc, JC), jb = min(ja + jc, JC);
       for (int jj = ja; jj < jb; ++jj) {
-        const float g = dg_s[jj * kLstmLd + b];
-        const float4* wr = reinterpret_cast<const float4*>(wt + (size_t)(j0 + jj) * 8);
-        const float4 w0 = wr[0], w1 = wr[1];
-        acc[0] = fmaf(w0.x, g, acc[0]); acc[1] = fmaf(w0.y, g, acc[1]);
-        acc[2] = fmaf(w0.z, g, acc[2]); acc[3] = fmaf(w0.w, g, acc[3]);
-        acc[4] = fmaf(w1.x, g, acc[4]); acc[5] = fmaf(w1.y, g, acc[5]);
-        acc[6] = fmaf(w1.z, g, acc[6]); acc[7] = fmaf(w1.w, g, acc[7]);
+        const float4 w4 = *reinterpret_cast<const float4*>(wt + (size_t)(j0 + jj) * 8 + ut);
+        const float4 g0 = *reinterpret_cast<const float4*>(dg_s + (size_t)jj * kLstmLd + bt);
+        const float4 g1 = *reinterpret_cast<const float4*>(dg_s + (size_t)jj * kLstmLd + bt + 4);
+        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(w[i], g[j], acc[i][j]);
       }
       __syncthreads();   // everyone is done with this buffer before it is refilled two chunks later
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) red[((size_t)slice * 8 + i) * kLstmMaxB + b] = acc[i];
+    for (int i = 0; i < 4; ++i) {
+      float* rr = red + ((size_t)jslice * 8 + ut + i) * kLstmMaxB + bt;
+      *reinterpret_cast<float4*>(rr) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(rr + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
     __syncthreads();
     float d4[4] = {0.f, 0.f, 0.f, 0.f};
     if (mine) {
       const int u = u0 + ul_own;
 #pragma unroll
-      for (int sl = 0; sl < 8; ++sl) dh += red[((size_t)sl * 8 + ul_own) * kLstmMaxB + b];
+      for (int sl = 0; sl < 32; ++sl) dh += red[((size_t)sl * 8 + ul_own) * kLstmMaxB + b];
       float di = 0.f, df = 0.f, dg = 0.f, dout = 0.f;
       if (on) {
         const float tc = tanhf(cn);
@@ -345,7 +368,7 @@ extern "C" int radtts_lstm_forward(const float* gx, const float* whh, const int*
   RB_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)4 * 32 * H * sizeof(float), st));
   RB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
   const int R = 4 * d.U;
-  const size_t smem = ((size_t)H * R + (size_t)H * kLstmLd + (size_t)8 * R * kLstmMaxB) * sizeof(float);
+  const size_t smem = ((size_t)H * R + (size_t)H * kLstmLd + (size_t)16 * R * kLstmMaxB) * sizeof(float);
   if (smem > (size_t)kSmemBudget) return RADTTS_ERR_UNSUPPORTED;
   static size_t configured = 0;
   if (smem > configured) {
@@ -372,7 +395,8 @@ extern "C" int radtts_lstm_backward(const float* dh_all, const float* whh, const
   unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * 32 * H * sizeof(float));
   RB_CUDA(cudaMemsetAsync(dgbuf, 0, (size_t)16 * 32 * H * sizeof(float), st));
   RB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
-  const size_t smem = ((size_t)4 * H * 8 + (size_t)2 * H * kLstmLd + (size_t)8 * 8 * kLstmMaxB) * sizeof(float);
+  if (H % 2) return RADTTS_ERR_UNSUPPORTED;
+  const size_t smem = ((size_t)4 * H * 8 + (size_t)2 * (H / 2) * kLstmLd + (size_t)32 * 8 * kLstmMaxB) * sizeof(float);
   if (smem > (size_t)kSmemBudget) return RADTTS_ERR_UNSUPPORTED;
   static size_t configured = 0;
   if (smem > configured) {
