@@ -268,6 +268,15 @@ RADTTS_API int radtts_attn_ctc(const float* attn_logprob, const int64_t* in_lens
                                int T2, float blank_logprob, float* losses, float* grad, void* ws, size_t ws_bytes,
                                void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused RAdam over a flat float32 parameter buffer (update rule of reference radam.py:76-116).
+ * p, g, m, v: device pointers to n floats (16-byte aligned); step_dev: device int64 counter (number of steps
+ * taken so far; incremented by the call); grad_scale: device scalar multiplied into g (clipping), or NULL.
+ * ---------------------------------------------------------------------------------------------- */
+RADTTS_API int radtts_radam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, long long* step_dev,
+                                 const float* grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

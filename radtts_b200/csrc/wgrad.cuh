@@ -123,29 +123,54 @@ inline int launch_wgrad_simt(const WgradProb& p, const int* plan, int rows_alloc
 }
 
 // out[n * ostride] += sum_r G[r, gcol + n] / (partial ? ratio(r) : 1)
+// Block = 128 columns x 8 row lanes, 4 consecutive columns per thread (one 8/16-byte load), 256-row chunks:
+// every warp reads whole 256/512-byte row segments, so the pass streams at HBM/L2 speed.
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+  v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ G, int ldg, int gcol, int N, RowMeta meta,
                                                      int partial, int log2d, int ksize, const int* __restrict__ plan,
                                                      int rows_alloc, int chunk, float* __restrict__ out, int ostride) {
   const int rows_used = plan ? plan[0] : rows_alloc;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + tx;
+  const int n0 = blockIdx.x * 128 + tx * 4;
   const int r_begin = blockIdx.y * chunk, r_end = min(r_begin + chunk, rows_used);
-  float s = 0.f;
-  if (n < N)
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (n0 < N) {   // N is a multiple of 4 for every caller (channel counts are multiples of 16)
+#pragma unroll 4
     for (int r = r_begin + ty; r < r_end; r += 8) {
-      float v = Act<T>::ld(G + (size_t)r * ldg + gcol + n);
-      if (partial && meta.valid(r)) v /= meta.ratio(r, log2d, ksize);
-      s += v;
-    }
-  __shared__ float red[8][33];
-  red[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && n < N) {
-    float t = 0.f;
+      float v[4];
+      load4<T>(G + (size_t)r * ldg + gcol + n0, v);
+      float sc = 1.f;
+      if (partial) sc = meta.valid(r) ? 1.f / meta.ratio(r, log2d, ksize) : 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][tx];
-    if (r_begin < r_end) atomicAdd(out + (size_t)n * ostride, t);
+      for (int i = 0; i < 4; ++i) s[i] = fmaf(v[i], sc, s[i]);
+    }
+  }
+  __shared__ float red[8][128 + 4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) red[ty][tx * 4 + i] = s[i];
+  __syncthreads();
+  if (threadIdx.x < 128 && r_begin < r_end) {
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+      atomicAdd(out + (size_t)n * ostride, t);
+    }
   }
 }
 
@@ -153,8 +178,9 @@ template <typename T>
 inline int launch_colsum(const T* G, int ldg, int gcol, int N, RowMeta meta, int partial, int log2d, int ksize,
                          const int* plan, int rows_alloc, float* out, int ostride, bool zero_first, cudaStream_t st) {
   if (zero_first) RB_CUDA(cudaMemsetAsync(out, 0, (size_t)N * ostride * sizeof(float), st));
-  const int chunk = 512;
-  dim3 grid(ceil_div(N, 32), ceil_div(rows_alloc, chunk));
+  if ((N % 4) || (ldg % 4) || (gcol % 4)) return RADTTS_ERR_INVALID_ARG;
+  const int chunk = 256;
+  dim3 grid(ceil_div(N, 128), ceil_div(rows_alloc, chunk));
   colsum_kernel<T><<<grid, 256, 0, st>>>(G, ldg, gcol, N, meta, partial, log2d, ksize, plan, rows_alloc, chunk, out, ostride);
   return after_launch();
 }

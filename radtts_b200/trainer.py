@@ -8,7 +8,8 @@ from . import loss as rloss
 
 class TrainStep:
     def __init__(self, model, loss_weights, lr=1e-4, weight_decay=1e-6, grad_clip_val=1.0, bf16=True,
-                 binarize_attention=True, use_binarization_loss=True, ddp=False, device_ids=None, capturable=False):
+                 binarize_attention=True, use_binarization_loss=True, ddp=False, device_ids=None, capturable=False,
+                 fused_optimizer=True):
         self.raw_model = model
         self.model = model
         if ddp:
@@ -23,8 +24,13 @@ class TrainStep:
         self.grad_clip_val = grad_clip_val
         params = [p for p in model.parameters() if p.requires_grad]
         self.capturable = bool(capturable)
-        self.optimizer = torch.optim.RAdam(params, lr=lr, weight_decay=weight_decay, foreach=True,
-                                           capturable=self.capturable)
+        self.fused_optimizer = bool(fused_optimizer) and not ddp
+        if self.fused_optimizer:
+            from .optim import FusedRAdam
+            self.optimizer = FusedRAdam(params, lr=lr, weight_decay=weight_decay)
+        else:
+            self.optimizer = torch.optim.RAdam(params, lr=lr, weight_decay=weight_decay, foreach=True,
+                                               capturable=self.capturable)
         self.graph = None
         self.launches_per_replay = 0
         self.static_batch = None
@@ -75,10 +81,14 @@ class TrainStep:
         return self._eager_step(batch)
 
     def _eager_step(self, batch):
-        self.optimizer.zero_grad(set_to_none=True)
+        self.optimizer.zero_grad(set_to_none=not self.fused_optimizer)
         total, _ = self.forward_loss(batch)
         total.backward()
-        if self.grad_clip_val > 0:
-            torch.nn.utils.clip_grad_norm_(self.raw_model.parameters(), self.grad_clip_val, foreach=True)
-        self.optimizer.step()
+        if self.fused_optimizer:
+            scale = self.optimizer.clip_coefficient(self.grad_clip_val) if self.grad_clip_val > 0 else None
+            self.optimizer.step(scale)
+        else:
+            if self.grad_clip_val > 0:
+                torch.nn.utils.clip_grad_norm_(self.raw_model.parameters(), self.grad_clip_val, foreach=True)
+            self.optimizer.step()
         return total.detach()
