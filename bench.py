@@ -234,7 +234,7 @@ def main():
     peaks = load_peaks()
 
     model = make_model(device).train()
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
     ts = TrainStep(model, configs.LOSS_WEIGHTS, bf16=True, ddp=world > 1, device_ids=[local] if world > 1 else None,
                    capturable=use_graph)
     host_batches = [pinned_batch(args.batch, args.t1, args.t2, seed=1000 + 17 * rank + i) for i in range(2)]
@@ -247,7 +247,7 @@ def main():
         except Exception as e:  # fall back to the eager step, say so in the JSON line
             graph_note = "eager (graph capture failed: %s)" % str(e).splitlines()[0][:120]
             torch.cuda.synchronize()
-            ts = TrainStep(model, configs.LOSS_WEIGHTS, bf16=True)
+            ts.graph = None
     frames_per_step_local = float(sum(int(b["out_lens"].sum()) for b in host_batches)) / len(host_batches)
     h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
 

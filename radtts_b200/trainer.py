@@ -12,9 +12,17 @@ class TrainStep:
                  fused_optimizer=True):
         self.raw_model = model
         self.model = model
+        self.world = 1
         if ddp:
-            from torch.nn.parallel import DistributedDataParallel as DDP
-            self.model = DDP(model, device_ids=device_ids, bucket_cap_mb=128, gradient_as_bucket_view=True)
+            import torch.distributed as dist
+            self.world = dist.get_world_size()
+            if not fused_optimizer:
+                from torch.nn.parallel import DistributedDataParallel as DDP
+                self.model = DDP(model, device_ids=device_ids, bucket_cap_mb=128, gradient_as_bucket_view=True)
+            else:
+                # replicas start identical (reference distributed.py:111-114 broadcasts every tensor from rank 0)
+                for t in list(model.parameters()) + list(model.buffers()):
+                    dist.broadcast(t.data, 0)
         self.criterion = rloss.RADTTSLoss(sigma=1.0, n_group_size=model.n_group_size, loss_weights=loss_weights)
         self.bin_loss = rloss.AttentionBinarizationLoss()
         self.loss_weights = loss_weights
@@ -24,7 +32,7 @@ class TrainStep:
         self.grad_clip_val = grad_clip_val
         params = [p for p in model.parameters() if p.requires_grad]
         self.capturable = bool(capturable)
-        self.fused_optimizer = bool(fused_optimizer) and not ddp
+        self.fused_optimizer = bool(fused_optimizer)
         if self.fused_optimizer:
             from .optim import FusedRAdam
             self.optimizer = FusedRAdam(params, lr=lr, weight_decay=weight_decay)
@@ -85,7 +93,19 @@ class TrainStep:
         total, _ = self.forward_loss(batch)
         total.backward()
         if self.fused_optimizer:
-            scale = self.optimizer.clip_coefficient(self.grad_clip_val) if self.grad_clip_val > 0 else None
+            if self.world > 1:
+                # data-parallel gradient exchange on the flat buffer: the reference does one flat all-reduce after
+                # backward (distributed.py:133-140); chunks let NCCL pipeline over NVLink / NVSwitch
+                import torch.distributed as dist
+                for chunk in self.optimizer.grad.split(32 << 20):
+                    dist.all_reduce(chunk)
+            if self.grad_clip_val > 0:
+                # the buffer holds the SUM over ranks: ||mean|| = ||sum|| / world, and the mean itself is folded
+                # into the scale the optimizer kernel applies
+                norm = torch.linalg.vector_norm(self.optimizer.grad) / self.world
+                scale = ((self.grad_clip_val / (norm + 1e-6)).clamp(max=1.0) / self.world).reshape(1)
+            else:
+                scale = torch.full((1,), 1.0 / self.world, device=self.optimizer.grad.device) if self.world > 1 else None
             self.optimizer.step(scale)
         else:
             if self.grad_clip_val > 0:
