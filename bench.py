@@ -234,7 +234,7 @@ def main():
     peaks = load_peaks()
 
     model = make_model(device).train()
-    use_graph = (world == 1) and not args.no_graph   # NCCL collectives inside a captured step hung in testing: eager at N > 1
+    use_graph = not args.no_graph   # N > 1: two graphs with the NCCL all-reduce launched eagerly in between
     ts = TrainStep(model, configs.LOSS_WEIGHTS, bf16=True, ddp=world > 1, device_ids=[local] if world > 1 else None,
                    capturable=use_graph)
     host_batches = [pinned_batch(args.batch, args.t1, args.t2, seed=1000 + 17 * rank + i) for i in range(2)]

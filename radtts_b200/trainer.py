@@ -40,6 +40,7 @@ class TrainStep:
             self.optimizer = torch.optim.RAdam(params, lr=lr, weight_decay=weight_decay, foreach=True,
                                                capturable=self.capturable)
         self.graph = None
+        self.graph_update = None
         self.launches_per_replay = 0
         self.static_batch = None
         self.static_loss = None
@@ -60,10 +61,13 @@ class TrainStep:
         return total, out
 
     def capture(self, example_batch, warmup=3):
-        """Captures the whole step (forward, losses, backward, clip, RAdam) into one CUDA graph.  Possible because the
-        step has no host synchronisation left (device-side frame plans, fused CTC, persistent LSTM); requires a fixed
-        batch shape -- lengths stay device data and may change from replay to replay."""
-        assert self.capturable, "construct TrainStep(capturable=True) to use CUDA graphs"
+        """Captures the step into CUDA graphs.  Possible because the step has no host synchronisation left
+        (device-side frame plans, fused CTC, persistent LSTM); requires a fixed batch shape -- lengths stay device
+        data and may change from replay to replay.
+        One process: ONE graph (forward, losses, backward, clip, RAdam).  Data parallel: TWO graphs with the NCCL
+        gradient all-reduce launched eagerly between them (collectives inside a capture hung in testing)."""
+        assert self.capturable and self.fused_optimizer, "CUDA graphs need TrainStep(capturable=True, fused_optimizer=True)"
+        from . import _lib
         self.static_batch = {k: v.clone() for k, v in example_batch.items()}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -72,43 +76,64 @@ class TrainStep:
                 self._eager_step(self.static_batch)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        from . import _lib
-        graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
+        graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.static_loss = self._eager_step(self.static_batch)
-        self.launches_per_replay = _lib.launch_count() - n0   # kernels of libradtts_b200.so inside one replay
+            self.static_loss = self._fwd_bwd(self.static_batch)
+            if self.world == 1:
+                self._update()
         self.graph = graph
+        if self.world > 1:
+            self.graph_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_update, pool=graph.pool()):
+                self._update()
+        self.launches_per_replay = _lib.launch_count() - n0   # kernels of libradtts_b200.so inside one replay
 
     def step(self, batch):
         if self.graph is not None:
             for k, v in batch.items():
                 self.static_batch[k].copy_(v, non_blocking=True)
             self.graph.replay()
+            if self.world > 1:
+                self._allreduce()
+                self.graph_update.replay()
             return self.static_loss
         return self._eager_step(batch)
 
-    def _eager_step(self, batch):
+    def _fwd_bwd(self, batch):
         self.optimizer.zero_grad(set_to_none=not self.fused_optimizer)
         total, _ = self.forward_loss(batch)
         total.backward()
-        if self.fused_optimizer:
-            if self.world > 1:
-                # data-parallel gradient exchange on the flat buffer: the reference does one flat all-reduce after
-                # backward (distributed.py:133-140); chunks let NCCL pipeline over NVLink / NVSwitch
-                import torch.distributed as dist
-                for chunk in self.optimizer.grad.split(32 << 20):
-                    dist.all_reduce(chunk)
-            if self.grad_clip_val > 0:
-                # the buffer holds the SUM over ranks: ||mean|| = ||sum|| / world, and the mean itself is folded
-                # into the scale the optimizer kernel applies
-                norm = torch.linalg.vector_norm(self.optimizer.grad) / self.world
-                scale = ((self.grad_clip_val / (norm + 1e-6)).clamp(max=1.0) / self.world).reshape(1)
-            else:
-                scale = torch.full((1,), 1.0 / self.world, device=self.optimizer.grad.device) if self.world > 1 else None
-            self.optimizer.step(scale)
+        return total.detach()
+
+    def _allreduce(self):
+        # data-parallel gradient exchange on the flat buffer: the reference does one flat all-reduce after backward
+        # (distributed.py:133-140); 128 MB chunks let NCCL pipeline over NVLink / NVSwitch
+        import torch.distributed as dist
+        for chunk in self.optimizer.grad.split(32 << 20):
+            dist.all_reduce(chunk)
+
+    def _update(self):
+        if self.grad_clip_val > 0:
+            # with data parallelism the buffer holds the SUM over ranks: ||mean|| = ||sum|| / world, and the mean
+            # itself is folded into the scale the optimizer kernel applies
+            norm = torch.linalg.vector_norm(self.optimizer.grad) / self.world
+            scale = ((self.grad_clip_val / (norm + 1e-6)).clamp(max=1.0) / self.world).reshape(1)
         else:
-            if self.grad_clip_val > 0:
-                torch.nn.utils.clip_grad_norm_(self.raw_model.parameters(), self.grad_clip_val, foreach=True)
-            self.optimizer.step()
+            scale = torch.full((1,), 1.0 / self.world, device=self.optimizer.grad.device) if self.world > 1 else None
+        self.optimizer.step(scale)
+
+    def _eager_step(self, batch):
+        if self.fused_optimizer:
+            loss = self._fwd_bwd(batch)
+            if self.world > 1:
+                self._allreduce()
+            self._update()
+            return loss
+        self.optimizer.zero_grad(set_to_none=True)
+        total, _ = self.forward_loss(batch)
+        total.backward()
+        if self.grad_clip_val > 0:
+            torch.nn.utils.clip_grad_norm_(self.raw_model.parameters(), self.grad_clip_val, foreach=True)
+        self.optimizer.step()
         return total.detach()
