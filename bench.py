@@ -172,6 +172,51 @@ def in_layer_kernel_probe(model, batch, iters=10):
     return e0.elapsed_time(e1) / iters, groups
 
 
+def _time_ms(fn, iters, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def extras(model, batch, peaks):
+    """The other two numbers BASELINE.json's metric names: batched decoder inference (frames/s) and MAS ms/batch."""
+    from radtts_b200 import alignment, ops
+    out = {}
+    dev = batch["mel"].device
+    B, _, T1 = batch["mel"].shape
+    g = model.n_group_size
+    frames = int(batch["out_lens"].sum())
+    was_training = model.training
+    model.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ctx = torch.randn(B, 1040, T1 // g, device=dev) * 0.5
+        residual = torch.randn(B, 80 * g, T1 // g, device=dev) * 0.8
+        ms = _time_ms(lambda: ops.decoder_inverse(model, residual, ctx, batch["out_lens"]), 5)
+        out["infer_decoder"] = {"value": round(frames / ms * 1e3, 1), "unit": "mel frames/s", "ms": round(ms, 3),
+                                "what": "8-flow decoder sampling direction (config_ljs_radtts), bf16, batch %d x <=%d frames, "
+                                        "conditioning given" % (B, T1),
+                                "frac_of_bf16_burst_peak": round(frames * FLOP_PER_FRAME_FWD / ms / 1e9 / peaks["tf_burst"], 4)}
+    model.train(was_training)
+    for (b, t1, t2) in ((B, T1, batch["text"].shape[1]), (64, 2000, 300)):
+        gen = torch.Generator(device=dev).manual_seed(0)
+        attn = torch.rand((b, 1, t1, t2), device=dev, generator=gen).add_(1e-6)
+        logp = torch.log(attn / attn.sum(3, keepdim=True))
+        il = torch.full((b,), t2, dtype=torch.int64, device=dev)
+        ol = torch.full((b,), t1, dtype=torch.int64, device=dev)
+        ms = _time_ms(lambda: alignment.mas_forward(logp, il, ol, is_prob=False), 10)
+        gbs = b * t1 * t2 * 8 / ms / 1e6
+        out["mas_%dx%dx%d" % (b, t1, t2)] = {"ms_per_batch": round(ms, 4), "GBps": round(gbs, 1),
+                                              "frac_hbm": round(gbs / peaks["hbm_gbs"], 4)}
+    return out
+
+
 def cpu_baseline(B, T1, T2, steps=1, warmup=0):
     """The oracle port of the reference hot path on the host cores (bounded sample)."""
     from oracle import train_step as ots
@@ -296,6 +341,12 @@ def main():
                     "frac": round(achieved / peaks["tf_burst"], 4), "traffic": None, "peak_source": peaks["source"] + " burst",
                     "ms_per_launch": round(k_ms, 4),
                     "step_frac_of_sustained_peak": round(value / world * FLOP_PER_FRAME_TRAIN / 1e12 / peaks["tf_sustained"], 4)}
+    extra = None
+    if rank == 0 and world == 1:
+        try:
+            extra = extras(model, dev_batches[0], peaks)
+        except Exception as e:
+            extra = {"error": repr(e)}
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -312,7 +363,7 @@ def main():
                 "e2e": {"value": round(e2e_value, 1), "unit": "mel frames/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
                 "gpu_launches": int(launches * world), "clocks": clocks, "roofline": roofline, "cpu_baseline": cb,
-                "loss_last": losses[-1] if losses else None}
+                "loss_last": losses[-1] if losses else None, "extra": extra}
         line["config"]["global_batch"] = args.batch * world
         line["config"]["execution"] = graph_note
         print(json.dumps(line))

@@ -329,8 +329,10 @@ class _FlowStackFn(torch.autograd.Function):
         saved = [None] * len(dims_list)
         for i in order:
             dims = dims_list[i]
-            w_i = ws[i * n_per_flow:(i + 1) * n_per_flow]
-            blob = prepare_flow(dims, w_i, prec, need_bwd, z.device)
+            if n_per_flow == 0:
+                blob = ws[i]                                   # cached, already prepared (inference)
+            else:
+                blob = prepare_flow(dims, ws[i * n_per_flow:(i + 1) * n_per_flow], prec, need_bwd, z.device)
             lease = _Lease()
             zout, log_s, bufs, _ = run_flowstep(dims, blob, plan, z, ctx_packed, prec, inverse, lease, need_bwd)
             if need_bwd:
@@ -355,16 +357,36 @@ def ctx_ld_of(n_ctx):
     return (n_ctx + 63) // 64 * 64
 
 
+_blob_cache = {}
+
+
+def _cached_blob(flow, dims, prec, inverse, device):
+    key = (id(flow), prec, bool(inverse), dims.c_off, device.index)
+    versions = tuple(p._version for p in flow.parameters())
+    hit = _blob_cache.get(key)
+    if hit is not None and hit[0] == versions:
+        return hit[1]
+    with torch.no_grad():
+        blob = prepare_flow(dims, _flow_weight_list(flow, inverse), prec, False, device)
+    _blob_cache[key] = (versions, blob)
+    return blob
+
+
 def flow_stack_packed(flows, zin, ctx_packed, plan, z_ld, actives, inverse=False, prec=None):
     """Runs `flows` (in order; reversed when inverse) on packed rows.  actives[i] = channels flow i transforms."""
     prec = current_precision() if prec is None else prec
     dims_list = [_flow_dims(f, z_ld, c) for f, c in zip(flows, actives)]
-    ws = []
-    for f in flows:
-        w = _flow_weight_list(f, inverse)
-        ws += w
-    n_per = len(ws) // len(flows)
-    out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, n_per, *ws)
+    if not torch.is_grad_enabled():
+        # inference: weights are frozen between calls -> the re-laid-out blobs are cached per flow (keyed on the
+        # parameters' version counters), and neither weight norm nor W^-1 nor the re-layout run again
+        blobs = [_cached_blob(f, d, prec, inverse, zin.device) for f, d in zip(flows, dims_list)]
+        out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, 0, *blobs)
+    else:
+        ws = []
+        for f in flows:
+            ws += _flow_weight_list(f, inverse)
+        n_per = len(ws) // len(flows)
+        out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, n_per, *ws)
     if inverse:
         return out
     zout, log_s = out[0], list(out[1:])
