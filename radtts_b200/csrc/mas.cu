@@ -2,16 +2,19 @@
 //
 // Replaces RADTTS.binarize_attention (reference radtts.py:320-334) + alignment.mas_width1 (reference
 // alignment.py:31-59).  One CTA per utterance:
-//   warp 1   : TMA producer -- streams the utterance's (out_len x T2) cost rows HBM -> smem ring with 1-D
-//              bulk async copies (cp.async.bulk + mbarrier), many KB in flight per SM;
-//   warp 0   : dynamic-programming warp -- each lane owns NC consecutive text columns in registers; the
-//              j-1 neighbour of a lane's first column comes from one __shfl_up per row (off the critical
-//              path); the `diagonal` decision of every cell is kept as ONE BIT (warp ballot) in smem;
-//   warps 2-7: zero-fill the utterance's slab of the dense hard map while the DP runs;
-//   then lane 0 backtracks through the bit lattice and all threads scatter the ones, frame->token
-//   indices and durations.
-// Arithmetic is exactly the reference's: one fp32 add per cell, `>=` tie-break toward the diagonal,
-// row 0 restricted to column 0, and the unconditional opt[0,0] = 1 (alignment.py:59).
+//   producer warp : streams the utterance's (out_len x T2) cost rows HBM -> smem ring with 1-D bulk async copies
+//                   (cp.async.bulk + mbarrier), many KB in flight per SM;
+//   W DP warps    : warp w owns text columns [32w, 32w+32), one column per lane, its running score in a register.
+//                   Row i needs only row i-1 (columns j-1, j): inside a warp that is one __shfl_up; across warps the
+//                   last lane's score goes through a small smem ring and warp w simply trails warp w-1 by a few rows
+//                   (skewed wavefront, no CTA-wide barrier in the loop).  The diagonal/straight decision of every
+//                   cell is ONE BIT: a warp ballot per row yields the 32 decisions of the warp's columns as one word,
+//                   already in natural column order;
+//   fill warps    : zero the utterance's slab of the dense hard map while the DP runs;
+//   then warp 0 backtracks 32 rows at a time with the bit windows held in registers (no dependent smem latency per
+//   step), and all threads scatter the ones, frame->token indices and durations.
+// Arithmetic is exactly the reference's: one fp32 add per cell, `>=` tie-break toward the diagonal, row 0 restricted
+// to column 0, and the unconditional opt[0,0] = 1 (alignment.py:59).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -19,44 +22,48 @@
 
 namespace rb {
 
-constexpr int kMasThreads = 256;
-constexpr int kMasMaxStages = 16;
-constexpr int kMasHeaderBytes = 2 * kMasMaxStages * 8;
+constexpr int kMasMaxDpWarps = 18;   // T2 <= 576
+constexpr int kMasFillWarps = 4;
+constexpr int kMasMaxStages = 32;
+constexpr int kMasEdge = 128;        // rows of slack in the inter-warp edge ring
 
 struct MasPlan {
-  int nc;               // columns per lane (odd -> conflict-free smem reads)
-  int rows_per_chunk;   // rows per bulk copy
-  int stages;           // ring depth
+  int W;                // DP warps
+  int threads;
+  int rows_per_chunk;   // rows per bulk copy (= progress-publication granularity)
+  int stages;
   uint32_t stage_bytes;
-  uint32_t path_off, dur_off, bits_off, ring_off, smem_bytes;
+  uint32_t path_off, dur_off, edge_off, bits_off, ring_off, smem_bytes;
   int bits_in_smem;
-  size_t bits_ws_bytes;  // global fallback for the bit lattice
+  size_t bits_ws_bytes;
 };
 
 static int make_plan(int B, int T1, int T2, MasPlan* p) {
-  int nc = (T2 + 31) / 32;
-  if (nc % 2 == 0) nc += 1;
-  if (nc > 17 || T1 > 65535) return RADTTS_ERR_UNSUPPORTED;
-  p->nc = nc;
-  int r = 12288 / (T2 * 4);
+  const int W = (T2 + 31) / 32;
+  if (W > kMasMaxDpWarps || T1 > 65535) return RADTTS_ERR_UNSUPPORTED;
+  p->W = W;
+  p->threads = (W + 1 + kMasFillWarps) * 32;
+  int r = 6144 / (T2 * 4);
   if (r < 1) r = 1;
-  if (r > 64) r = 64;
+  if (r > 16) r = 16;
   p->rows_per_chunk = r;
   p->stage_bytes = (uint32_t)round_up(r * T2 * 4 + 32, 128);
-  p->path_off = kMasHeaderBytes;
-  p->dur_off = p->path_off + (uint32_t)round_up(T1 * 2, 16);
-  p->bits_off = p->dur_off + (uint32_t)round_up(T2 * 4, 16);
-  uint32_t bits_bytes = (uint32_t)round_up(T1 * nc * 4, 128);
-  uint32_t fixed = (uint32_t)round_up((int)p->bits_off, 128);
-  p->bits_off = fixed;
-  if (fixed + bits_bytes + 3 * p->stage_bytes <= (uint32_t)kSmemBudget) {
+  uint32_t off = 2 * kMasMaxStages * 8 + 256;            // mbarriers + progress counters
+  p->path_off = off;            off += (uint32_t)round_up(T1 * 2, 16);
+  p->dur_off = off;             off += (uint32_t)round_up(T2 * 4, 16);
+  p->edge_off = off;            off += (uint32_t)(W * kMasEdge * 4);
+  off = (uint32_t)round_up((int)off, 128);
+  p->bits_off = off;
+  const uint32_t bits_bytes = (uint32_t)round_up(T1 * W * 4, 128);
+  const uint32_t need_stages = (uint32_t)(W + 2);         // the wavefront skew is ~1 chunk per DP warp
+  if (off + bits_bytes + need_stages * p->stage_bytes <= (uint32_t)kSmemBudget) {
     p->bits_in_smem = 1;
-    p->ring_off = fixed + bits_bytes;
+    p->ring_off = off + bits_bytes;
     p->bits_ws_bytes = 0;
   } else {
     p->bits_in_smem = 0;
-    p->ring_off = fixed;
-    p->bits_ws_bytes = (size_t)B * T1 * nc * 4;
+    p->ring_off = off;
+    p->bits_ws_bytes = (size_t)B * T1 * W * 4;
   }
   int st = (int)((kSmemBudget - p->ring_off) / p->stage_bytes);
   if (st > kMasMaxStages) st = kMasMaxStages;
@@ -66,9 +73,7 @@ static int make_plan(int B, int T1, int T2, MasPlan* p) {
   return 0;
 }
 
-// ---------------------------------------------------------------------------------------------
 // Optional pre-pass for probability input: y = logf(x).  (HBM-bound, all SMs.)
-// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mas_log_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -84,7 +89,6 @@ __global__ void __launch_bounds__(256) mas_log_kernel(const float* __restrict__ 
 }
 
 __device__ __forceinline__ void zero_fill(float* p, size_t n, int tid, int nthreads) {
-  // head to 16-byte alignment, float4 body, scalar tail
   size_t head = ((16 - ((uintptr_t)p & 15)) & 15) / 4;
   if (head > n) head = n;
   for (size_t k = tid; k < head; k += nthreads) p[k] = 0.f;
@@ -95,44 +99,60 @@ __device__ __forceinline__ void zero_fill(float* p, size_t n, int tid, int nthre
   for (size_t k = head + n4 * 4 + tid; k < n; k += nthreads) p[k] = 0.f;
 }
 
-template <int NC>
-__global__ void __launch_bounds__(kMasThreads, 1)
+__device__ __forceinline__ int ld_volatile_s32(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_s32(int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__((kMasMaxDpWarps + 1 + kMasFillWarps) * 32, 1)
 mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, const int64_t* __restrict__ out_lens,
            int T1, int T2, unsigned long long total_bytes, float* __restrict__ hard, int32_t* __restrict__ f2t,
            int32_t* __restrict__ dur, uint32_t* __restrict__ bits_ws, MasPlan plan) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMasMaxStages;
+  int* done = reinterpret_cast<int*>(smem + 2 * kMasMaxStages * 8);   // done[w] = rows finished by DP warp w
   uint16_t* path = reinterpret_cast<uint16_t*>(smem + plan.path_off);
   int* dur_s = reinterpret_cast<int*>(smem + plan.dur_off);
+  float* edge = reinterpret_cast<float*>(smem + plan.edge_off);      // [W][kMasEdge]
   uint8_t* ring = smem + plan.ring_off;
 
   const int b = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
+  const int W = plan.W;
   long long ol = out_lens[b], il = in_lens[b];
   const int olen = (int)(ol < 0 ? 0 : (ol > T1 ? T1 : ol));
   const int ilen = (int)(il < 0 ? 0 : (il > T2 ? T2 : il));
   uint32_t* bits = plan.bits_in_smem ? reinterpret_cast<uint32_t*>(smem + plan.bits_off)
-                                     : bits_ws + (size_t)b * T1 * NC;
+                                     : bits_ws + (size_t)b * T1 * W;
   const int R = plan.rows_per_chunk;
   const int stages = plan.stages;
   const bool active = (olen > 0 && ilen > 0);
   const int nchunks = active ? (olen + R - 1) / R : 0;
+  // only the warps that hold live columns take part in the DP
+  const int Wl = active ? (ilen + 31) / 32 : 0;
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], (uint32_t)(Wl > 0 ? Wl : 1));
     }
     mbar_fence_init();
   }
-  for (int j = tid; j < T2; j += kMasThreads) dur_s[j] = 0;
+  for (int j = tid; j < T2; j += nthreads) dur_s[j] = 0;
+  if (tid < 64) done[tid] = 0;
+  if (active)
+    for (int j = tid; j < W; j += nthreads) bits[j] = 0u;   // row 0 carries no decisions
   __syncthreads();
 
   const size_t slab = (size_t)b * T1 * T2;
 
-  if (warp == 1) {
+  if (warp == W) {
     // ------------------------------ producer ------------------------------
     if (lane == 0) {
       const unsigned long long total16 = total_bytes & ~15ull;
@@ -149,122 +169,114 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
         if (e16 > total16) e16 = total16;
         uint8_t* dst = ring + (size_t)s * plan.stage_bytes;
         const uint32_t nbytes = e16 > s16 ? (uint32_t)(e16 - s16) : 0u;
-        // bytes past the last 16-byte boundary of the tensor (at most 12) are fetched by hand
         const unsigned long long t0 = (s16 + nbytes > sb) ? (s16 + nbytes) : sb;
-        for (unsigned long long x = t0; x < eb; x += 4)
-          *reinterpret_cast<float*>(dst + (x - s16)) = *reinterpret_cast<const float*>(
-              reinterpret_cast<const uint8_t*>(logp) + x);
+        for (unsigned long long x = t0; x < eb; x += 4)   // at most 12 bytes past the last 16-byte boundary
+          *reinterpret_cast<float*>(dst + (x - s16)) =
+              *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(logp) + x);
         mbar_arrive_expect_tx(&full[s], nbytes);
         if (nbytes) bulk_g2s(dst, reinterpret_cast<const uint8_t*>(logp) + s16, nbytes, &full[s]);
       }
     }
-  } else if (warp == 0) {
-    // ------------------------------ DP warp ------------------------------
-    if (active) {
-      float v[NC];
-      int off[NC];
-#pragma unroll
-      for (int c = 0; c < NC; ++c) off[c] = min(lane * NC + c, T2 - 1);
+  } else if (warp < W) {
+    // ------------------------------ DP warps (skewed wavefront) ------------------------------
+    if (warp < Wl) {
+      const int col = warp * 32 + lane;
+      const int ccol = min(col, T2 - 1);
       const float nanv = __int_as_float(0x7fc00000);
-      int row = 0;
+      float v = -CUDART_INF_F;
+      int up_seen = 0;                       // rows warp-1 is known to have finished
+      int down_seen = 0;                     // rows warp+1 is known to have finished (back-pressure on the edge ring)
+      float* my_edge = edge + (size_t)warp * kMasEdge;
+      const float* up_edge = edge + (size_t)(warp > 0 ? warp - 1 : 0) * kMasEdge;
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % stages;
-        mbar_wait(&full[s], (uint32_t)((c / stages) & 1));
         const int r0 = c * R;
         const int r1 = min(r0 + R, olen);
+        // row i of this warp needs row i-1 of warp-1 (its last lane): wait until warp-1 has finished rows < r1 - 1
+        if (warp > 0) {
+          while (up_seen < r1 - 1) up_seen = ld_volatile_s32(&done[warp - 1]);
+          __threadfence_block();
+        }
+        if (warp + 1 < Wl) {
+          while (r1 - down_seen > kMasEdge - 1) down_seen = ld_volatile_s32(&done[warp + 1]);
+        }
+        mbar_wait(&full[s], (uint32_t)((c / stages) & 1));
         const unsigned long long sb = (unsigned long long)(slab + (size_t)r0 * T2) * 4ull;
         const float* st = reinterpret_cast<const float*>(ring + (size_t)s * plan.stage_bytes + (sb & 15ull));
-        float a[NC];
-#pragma unroll
-        for (int cc = 0; cc < NC; ++cc) a[cc] = st[off[cc]];
-        for (; row < r1; ++row) {
-          float an[NC];
-          const float* nx = st + (size_t)(row + 1 - r0) * T2;
-          if (row + 1 < r1) {
-#pragma unroll
-            for (int cc = 0; cc < NC; ++cc) an[cc] = nx[off[cc]];
-          } else {
-#pragma unroll
-            for (int cc = 0; cc < NC; ++cc) an[cc] = 0.f;
-          }
+        float a = st[ccol];
+        for (int row = r0; row < r1; ++row) {
+          const float an = (row + 1 < r1) ? st[(size_t)(row + 1 - r0) * T2 + ccol] : 0.f;
           if (row == 0) {
-#pragma unroll
-            for (int cc = 0; cc < NC; ++cc) v[cc] = (lane * NC + cc == 0) ? a[cc] : -CUDART_INF_F;
+            v = (col == 0) ? a : -CUDART_INF_F;
           } else {
-            float left = __shfl_up_sync(0xffffffffu, v[NC - 1], 1);
-            if (lane == 0) left = nanv;  // column 0 has no diagonal predecessor: NaN >= x is false
-            uint32_t mine = 0;
-#pragma unroll
-            for (int cc = NC - 1; cc >= 0; --cc) {
-              const float l = (cc == 0) ? left : v[cc - 1];
-              const float u = v[cc];
-              const bool diag = (l >= u);
-              const float m = diag ? l : u;
-              v[cc] = __fadd_rn(a[cc], m);
-              const uint32_t w = __ballot_sync(0xffffffffu, diag);
-              if (lane == cc) mine = w;
-            }
-            if (lane < NC) bits[(size_t)row * NC + lane] = mine;
+            float left = __shfl_up_sync(0xffffffffu, v, 1);
+            if (lane == 0) left = (warp == 0) ? nanv : up_edge[(row - 1) & (kMasEdge - 1)];  // NaN >= x is false
+            const bool diag = (left >= v);
+            v = __fadd_rn(a, diag ? left : v);
+            const uint32_t w = __ballot_sync(0xffffffffu, diag);
+            if (lane == 0) bits[(size_t)row * W + warp] = w;
           }
-#pragma unroll
-          for (int cc = 0; cc < NC; ++cc) a[cc] = an[cc];
+          if (lane == 31) my_edge[row & (kMasEdge - 1)] = v;
+          a = an;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-      }
-      __syncwarp();
-      // ------------------------------ backtrack ------------------------------
-      if (lane == 0) {
-        int j = ilen - 1;
-        for (int i = olen - 1; i >= 1; --i) {
-          path[i] = (uint16_t)j;
-          const uint32_t w = bits[(size_t)i * NC + (j % NC)];
-          j -= (int)((w >> (j / NC)) & 1u);
+        if (lane == 0) {
+          mbar_arrive(&empty[s]);
+          __threadfence_block();
+          st_volatile_s32(&done[warp], r1);
         }
-        path[0] = (uint16_t)j;
       }
     }
   } else {
     // ------------------------------ zero fill ------------------------------
-    zero_fill(hard + slab, (size_t)T1 * T2, tid - 64, kMasThreads - 64);
+    zero_fill(hard + slab, (size_t)T1 * T2, tid - (W + 1) * 32, kMasFillWarps * 32);
+  }
+  __syncthreads();
+
+  // ------------------------------ backtrack: 32 rows per round, bit windows in registers ------------------------------
+  if (active && warp == 0) {
+    int j = ilen - 1;                                  // column at row `top`
+    for (int top = olen - 1; top >= 0; top -= 32) {
+      const int row = top - lane;                      // lane l looks at row top - l
+      uint32_t win = 0;                                // bit 31 <-> column j, bit k <-> column j - 31 + k
+      if (row >= 1) {
+        const int wj = j >> 5;
+        const uint32_t hi = bits[(size_t)row * W + wj];
+        const uint32_t lo = wj > 0 ? bits[(size_t)row * W + wj - 1] : 0u;
+        const unsigned long long x = ((unsigned long long)hi << 32) | lo;
+        win = (uint32_t)(x >> ((j & 31) + 1));
+      }
+      int pos = 31, mycol = 0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const uint32_t wk = __shfl_sync(0xffffffffu, win, k);
+        if (lane == k) mycol = j - (31 - pos);
+        pos -= (int)((wk >> pos) & 1u);                // rows <= 0 have win == 0: no movement
+      }
+      if (row >= 0) path[row] = (uint16_t)mycol;
+      j -= (31 - pos);
+    }
   }
   __syncthreads();
 
   // ------------------------------ scatter ------------------------------
   if (active) {
-    for (int i = tid; i < olen; i += kMasThreads) {
-      const int j = path[i];
-      hard[slab + (size_t)i * T2 + j] = 1.0f;
-      if (f2t) f2t[(size_t)b * T1 + i] = j;
-      atomicAdd(&dur_s[j], 1);
+    for (int i = tid; i < olen; i += nthreads) {
+      const int jj = path[i];
+      hard[slab + (size_t)i * T2 + jj] = 1.0f;
+      if (f2t) f2t[(size_t)b * T1 + i] = jj;
+      atomicAdd(&dur_s[jj], 1);
     }
-    if (tid == 0) {
-      hard[slab] = 1.0f;  // alignment.py:59
-    }
+    if (tid == 0) hard[slab] = 1.0f;  // alignment.py:59
   }
   if (f2t)
-    for (int i = olen + tid; i < T1; i += kMasThreads) f2t[(size_t)b * T1 + i] = -1;
+    for (int i = olen + tid; i < T1; i += nthreads) f2t[(size_t)b * T1 + i] = -1;
   __syncthreads();
   if (dur) {
     if (active && tid == 0 && path[0] != 0) dur_s[0] += 1;
     __syncthreads();
-    for (int j = tid; j < T2; j += kMasThreads) dur[(size_t)b * T2 + j] = dur_s[j];
+    for (int jj = tid; jj < T2; jj += nthreads) dur[(size_t)b * T2 + jj] = dur_s[jj];
   }
-}
-
-template <int NC>
-static int launch_mas(const float* logp, const int64_t* in_lens, const int64_t* out_lens, int B, int T1, int T2,
-                      float* hard, int32_t* f2t, int32_t* dur, uint32_t* bits_ws, const MasPlan& plan,
-                      cudaStream_t stream) {
-  static int configured_smem = 0;
-  if ((int)plan.smem_bytes > configured_smem) {
-    RB_CUDA(cudaFuncSetAttribute(mas_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    configured_smem = kSmemBudget;
-  }
-  const unsigned long long total_bytes = (unsigned long long)B * T1 * T2 * 4ull;
-  mas_kernel<NC><<<B, kMasThreads, plan.smem_bytes, stream>>>(logp, in_lens, out_lens, T1, T2, total_bytes, hard,
-                                                             f2t, dur, bits_ws, plan);
-  return after_launch();
 }
 
 }  // namespace rb
@@ -307,12 +319,13 @@ extern "C" int radtts_mas_forward(const float* attn, int is_prob, const int64_t*
     logp = lbuf;
   }
   uint32_t* bits_ws = plan.bits_in_smem ? nullptr : reinterpret_cast<uint32_t*>(wsp);
-  switch (plan.nc) {
-#define RB_MAS_CASE(N) \
-  case N: return launch_mas<N>(logp, in_lens, out_lens, B, T1, T2, attn_hard, frame_to_token, durations, bits_ws, plan, stream);
-    RB_MAS_CASE(1) RB_MAS_CASE(3) RB_MAS_CASE(5) RB_MAS_CASE(7) RB_MAS_CASE(9) RB_MAS_CASE(11) RB_MAS_CASE(13)
-    RB_MAS_CASE(15) RB_MAS_CASE(17)
-#undef RB_MAS_CASE
-    default: return RADTTS_ERR_UNSUPPORTED;
+  static bool configured = false;
+  if (!configured) {
+    RB_CUDA(cudaFuncSetAttribute(mas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured = true;
   }
+  const unsigned long long total_bytes = (unsigned long long)B * T1 * T2 * 4ull;
+  mas_kernel<<<B, plan.threads, plan.smem_bytes, stream>>>(logp, in_lens, out_lens, T1, T2, total_bytes, attn_hard,
+                                                          frame_to_token, durations, bits_ws, plan);
+  return after_launch();
 }
