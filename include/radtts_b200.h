@@ -63,6 +63,11 @@ RADTTS_API int radtts_mas_forward(const float* attn, int is_prob, const int64_t*
                        size_t ws_bytes, void* stream);
 
 
+/* Diagnostic: globaltimer (ns) phase marks of CTA 0 of the last radtts_mas_forward launch, copied to 8 host
+ * words: [0] start, [1] first DP warp done, [2] DP + fill done, [3] backtrack done, [4] end, [5] fill done.
+ * Synchronises the device. */
+RADTTS_API int radtts_mas_debug_timeline(unsigned long long* out8_host);
+
 /* ------------------------------------------------------------------------------------------------
  * Packed frame layout ("frame plan").
  * The reference keeps zero-padded (B, C, T') activations and re-derives masks with a host sync in every

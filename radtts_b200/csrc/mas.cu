@@ -43,11 +43,7 @@ static int make_plan(int B, int T1, int T2, MasPlan* p) {
   if (W > kMasMaxDpWarps || T1 > 65535) return RADTTS_ERR_UNSUPPORTED;
   p->W = W;
   p->threads = (W + 1 + kMasFillWarps) * 32;
-  int r = 6144 / (T2 * 4);
-  if (r < 1) r = 1;
-  if (r > 16) r = 16;
-  p->rows_per_chunk = r;
-  p->stage_bytes = (uint32_t)round_up(r * T2 * 4 + 32, 128);
+  int r = 1;
   uint32_t off = 2 * kMasMaxStages * 8 + 256;            // mbarriers + progress counters
   p->path_off = off;            off += (uint32_t)round_up(T1 * 2, 16);
   p->dur_off = off;             off += (uint32_t)round_up(T2 * 4, 16);
@@ -55,8 +51,9 @@ static int make_plan(int B, int T1, int T2, MasPlan* p) {
   off = (uint32_t)round_up((int)off, 128);
   p->bits_off = off;
   const uint32_t bits_bytes = (uint32_t)round_up(T1 * W * 4, 128);
-  const uint32_t need_stages = (uint32_t)(W + 2);         // the wavefront skew is ~1 chunk per DP warp
-  if (off + bits_bytes + need_stages * p->stage_bytes <= (uint32_t)kSmemBudget) {
+  const uint32_t need_stages = (uint32_t)(W + 3);         // the wavefront skew is one chunk per DP warp
+  auto stage_bytes_for = [&](int rows) { return (uint32_t)round_up(rows * T2 * 4 + 256, 128); };  // + alignment slack
+  if (off + bits_bytes + need_stages * stage_bytes_for(4) <= (uint32_t)kSmemBudget) {
     p->bits_in_smem = 1;
     p->ring_off = off + bits_bytes;
     p->bits_ws_bytes = 0;
@@ -65,6 +62,11 @@ static int make_plan(int B, int T1, int T2, MasPlan* p) {
     p->ring_off = off;
     p->bits_ws_bytes = (size_t)B * T1 * W * 4;
   }
+  // rows per chunk (= per-chunk synchronisation amortised over that many rows): as many as W+3 stages allow, <= 16
+  for (r = 16; r > 1; --r)
+    if (p->ring_off + need_stages * stage_bytes_for(r) <= (uint32_t)kSmemBudget) break;
+  p->rows_per_chunk = r;
+  p->stage_bytes = stage_bytes_for(r);
   int st = (int)((kSmemBudget - p->ring_off) / p->stage_bytes);
   if (st > kMasMaxStages) st = kMasMaxStages;
   if (st < 2) return RADTTS_ERR_UNSUPPORTED;
@@ -99,15 +101,138 @@ __device__ __forceinline__ void zero_fill(float* p, size_t n, int tid, int nthre
   for (size_t k = head + n4 * 4 + tid; k < n; k += nthreads) p[k] = 0.f;
 }
 
-__device__ __forceinline__ int ld_volatile_s32(const int* p) {
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
   int v;
-  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_volatile_s32(int* p, int v) {
-  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+__device__ __forceinline__ void st_release_s32(int* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_pred(uint32_t addr, uint32_t v, int pred) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.shared.b32 [%0], %1; }" ::"r"(addr), "r"(v), "r"(pred)
+               : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f32_pred(uint32_t addr, int pred, float otherwise) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q ld.shared.f32 %0, [%1]; }" : "+f"(otherwise) : "r"(addr), "r"(pred)
+               : "memory");
+  return otherwise;
+}
+__device__ __forceinline__ void st_global_pred(uint32_t* p, uint32_t v, int pred) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.global.b32 [%0], %1; }" ::"l"(p), "r"(v), "r"(pred) : "memory");
+}
+// producer-side wait with back-off: a tight try_wait spin slows the DP warps of the same SM by ~20 cycles per row
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(256);
+    if (++spins > (1u << 22)) __trap();
+  }
 }
 
+// phase timeline of CTA 0 (globaltimer ns): [0] start, [1] DP warp 0 done, [2] all DP/fill warps done, [3] backtrack
+// done, [4] end, [5] fill warps done.  Read back with radtts_mas_debug_timeline(); costs a handful of stores.
+__device__ unsigned long long g_mas_timeline[16];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One DP warp: columns [32 warp, 32 warp + 32) of the utterance, one per lane, R rows per ring stage.
+// Everything the row loop touches is addressed with 32-bit shared-window addresses computed once per chunk (a generic
+// pointer re-derives the window base with S2UR inside the loop), the stage index / phase are running counters (a
+// runtime `c % stages` costs ~130 cycles per chunk), and single-lane stores are PREDICATED, never branched: two
+// divergent single-lane branches in the row body cost ~120 cycles per row on sm_100 (tools/mas_micro.cu).
+template <bool kBitsInSmem, bool kFirstWarp>
+__device__ __forceinline__ void dp_warp(uint64_t* full, uint64_t* empty, int* done, float* edge, uint8_t* ring,
+                                        uint32_t* bits_s, uint32_t* bits_g, const MasPlan& plan, size_t slab, int T2,
+                                        int olen, int nchunks, int Wl, int warp, int lane, bool probe_cta) {
+  const int W = plan.W, R = plan.rows_per_chunk, stages = plan.stages;
+  const int col = warp * 32 + lane;
+  const int ccol = min(col, T2 - 1);
+  const float nanv = __int_as_float(0x7fc00000);
+  const int is_l0 = (lane == 0), is_l31 = (lane == 31);
+  const uint32_t row_bytes = (uint32_t)T2 * 4u;
+  const uint32_t my_edge = smem_u32(edge + (size_t)warp * kMasEdge);
+  const uint32_t up_edge = smem_u32(edge + (size_t)(kFirstWarp ? 0 : warp - 1) * kMasEdge);
+  const uint32_t bits_base = smem_u32(bits_s + warp);
+  const uint32_t ring_base = smem_u32(ring) + (uint32_t)ccol * 4u;
+  uint32_t mis = (uint32_t)((slab * 4) & 127);          // offset of the chunk's first byte inside its stage
+  const uint32_t mis_step = ((uint32_t)R * row_bytes) & 127u;
+  float v = -CUDART_INF_F;
+  int up_seen = 0;                       // rows warp-1 is known to have finished
+  int down_seen = 0;                     // rows warp+1 is known to have finished (back-pressure on the edge ring)
+  int s = 0;
+  uint32_t phase = 0;
+  long long tw_wait = 0, tw_rows = 0, tw_post = 0, tqs = clock64();
+  const bool probe = probe_cta && warp == Wl - 1 && lane == 0;
+  for (int c = 0, r0 = 0; c < nchunks; ++c, r0 += R) {
+    const int r1 = min(r0 + R, olen);
+    if constexpr (kFirstWarp) {
+      mbar_wait(&full[s], phase);
+    } else {
+      // row i needs row i-1 of warp-1 (its last lane): wait until warp-1 has finished this chunk.  Having seen that,
+      // the chunk's bytes are in the ring too (warp-1 waited on full[s], directly or transitively), so only warp 0
+      // polls the mbarrier.
+      while (up_seen < r1) up_seen = ld_acquire_s32(&done[warp - 1]);
+    }
+    if (warp + 1 < Wl) {
+      while (r1 - down_seen > kMasEdge - 1) down_seen = ld_acquire_s32(&done[warp + 1]);
+    }
+    const long long tq1 = clock64();
+    const uint32_t st = ring_base + (uint32_t)s * plan.stage_bytes + mis;
+    float a = lds_f32(st);
+    int row = r0;
+    if (row == 0) {                      // alignment.py:41-42: row 0 may only sit on token 0
+      v = (col == 0) ? a : -CUDART_INF_F;
+      st_shared_pred(my_edge, __float_as_uint(v), is_l31);
+      a = lds_f32(st + (uint32_t)min(1, r1 - 1) * row_bytes);
+      row = 1;
+    }
+    for (; row < r1; ++row) {
+      const float an = lds_f32(st + (uint32_t)(min(row + 1, r1 - 1) - r0) * row_bytes);   // clamped, never branched
+      float left = __shfl_up_sync(0xffffffffu, v, 1);
+      if constexpr (kFirstWarp) {
+        if (lane == 0) left = nanv;      // NaN >= x is false: column 0 never takes the diagonal
+      } else {
+        left = lds_f32_pred(up_edge + (uint32_t)((row - 1) & (kMasEdge - 1)) * 4u, is_l0, left);
+      }
+      const bool diag = (left >= v);
+      v = __fadd_rn(a, diag ? left : v);
+      const uint32_t w = __ballot_sync(0xffffffffu, diag);
+      if constexpr (kBitsInSmem) st_shared_pred(bits_base + (uint32_t)(row * W) * 4u, w, is_l0);
+      else st_global_pred(&bits_g[(size_t)row * W + warp], w, is_l0);
+      st_shared_pred(my_edge + (uint32_t)(row & (kMasEdge - 1)) * 4u, __float_as_uint(v), is_l31);
+      a = an;
+    }
+    const long long tq2 = clock64();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&empty[s]);
+      st_release_s32(&done[warp], r1);
+    }
+    if (++s == stages) { s = 0; phase ^= 1u; }
+    mis = (mis + mis_step) & 127u;
+    const long long tq3 = clock64();
+    if (probe) { tw_wait += tq1 - tqs; tw_rows += tq2 - tq1; tw_post += tq3 - tq2; }
+    tqs = tq3;
+  }
+  if (probe) {
+    g_mas_timeline[8] = tw_wait; g_mas_timeline[9] = tw_rows; g_mas_timeline[10] = tw_post;
+    g_mas_timeline[11] = nchunks; g_mas_timeline[12] = R;
+  }
+}
+
+// kBitsInSmem selects at COMPILE time where the bit lattice lives: a pointer chosen at run time between shared and
+// global memory compiles to generic ST.E / LD.E, and a generic store in the row loop cost ~300 cycles per DP row
+// (every following LDS waits for the generic address to resolve).
+template <bool kBitsInSmem>
 __global__ void __launch_bounds__((kMasMaxDpWarps + 1 + kMasFillWarps) * 32, 1)
 mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, const int64_t* __restrict__ out_lens,
            int T1, int T2, unsigned long long total_bytes, float* __restrict__ hard, int32_t* __restrict__ f2t,
@@ -128,8 +253,14 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
   long long ol = out_lens[b], il = in_lens[b];
   const int olen = (int)(ol < 0 ? 0 : (ol > T1 ? T1 : ol));
   const int ilen = (int)(il < 0 ? 0 : (il > T2 ? T2 : il));
-  uint32_t* bits = plan.bits_in_smem ? reinterpret_cast<uint32_t*>(smem + plan.bits_off)
-                                     : bits_ws + (size_t)b * T1 * W;
+  uint32_t* bits_s = reinterpret_cast<uint32_t*>(smem + plan.bits_off);
+  uint32_t* bits_g = bits_ws + (kBitsInSmem ? 0 : (size_t)b * T1 * plan.W);
+  auto put_bits = [&](size_t idx, uint32_t w) {
+    if constexpr (kBitsInSmem) bits_s[idx] = w; else bits_g[idx] = w;
+  };
+  auto get_bits = [&](size_t idx) -> uint32_t {
+    if constexpr (kBitsInSmem) return bits_s[idx]; else return bits_g[idx];
+  };
   const int R = plan.rows_per_chunk;
   const int stages = plan.stages;
   const bool active = (olen > 0 && ilen > 0);
@@ -147,10 +278,11 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
   for (int j = tid; j < T2; j += nthreads) dur_s[j] = 0;
   if (tid < 64) done[tid] = 0;
   if (active)
-    for (int j = tid; j < W; j += nthreads) bits[j] = 0u;   // row 0 carries no decisions
+    for (int j = tid; j < W; j += nthreads) put_bits(j, 0u);   // row 0 carries no decisions
   __syncthreads();
 
   const size_t slab = (size_t)b * T1 * T2;
+  if (b == 0 && tid == 0) { g_mas_timeline[0] = gtime(); g_mas_timeline[6] = (unsigned long long)clock64(); }
 
   if (warp == W) {
     // ------------------------------ producer ------------------------------
@@ -159,13 +291,15 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % stages;
         const int k = c / stages;
-        if (k > 0) mbar_wait(&empty[s], (uint32_t)((k & 1) ^ 1));
+        if (k > 0) mbar_wait_relaxed(&empty[s], (uint32_t)((k & 1) ^ 1));
         const int r0 = c * R;
         const int r1 = min(r0 + R, olen);
         const unsigned long long sb = (unsigned long long)(slab + (size_t)r0 * T2) * 4ull;
         const unsigned long long eb = (unsigned long long)(slab + (size_t)r1 * T2) * 4ull;
-        const unsigned long long s16 = sb & ~15ull;
-        unsigned long long e16 = (eb + 15ull) & ~15ull;
+        // 128-byte aligned source window: a bulk copy whose source is only 16-byte aligned runs at a fraction of the
+        // bandwidth (measured ~5 GB/s per SM), so fetch a few bytes more and index into the stage with the offset
+        const unsigned long long s16 = sb & ~127ull;
+        unsigned long long e16 = (eb + 127ull) & ~127ull;
         if (e16 > total16) e16 = total16;
         uint8_t* dst = ring + (size_t)s * plan.stage_bytes;
         const uint32_t nbytes = e16 > s16 ? (uint32_t)(e16 - s16) : 0u;
@@ -180,58 +314,21 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
   } else if (warp < W) {
     // ------------------------------ DP warps (skewed wavefront) ------------------------------
     if (warp < Wl) {
-      const int col = warp * 32 + lane;
-      const int ccol = min(col, T2 - 1);
-      const float nanv = __int_as_float(0x7fc00000);
-      float v = -CUDART_INF_F;
-      int up_seen = 0;                       // rows warp-1 is known to have finished
-      int down_seen = 0;                     // rows warp+1 is known to have finished (back-pressure on the edge ring)
-      float* my_edge = edge + (size_t)warp * kMasEdge;
-      const float* up_edge = edge + (size_t)(warp > 0 ? warp - 1 : 0) * kMasEdge;
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c % stages;
-        const int r0 = c * R;
-        const int r1 = min(r0 + R, olen);
-        // row i of this warp needs row i-1 of warp-1 (its last lane): wait until warp-1 has finished rows < r1 - 1
-        if (warp > 0) {
-          while (up_seen < r1 - 1) up_seen = ld_volatile_s32(&done[warp - 1]);
-          __threadfence_block();
-        }
-        if (warp + 1 < Wl) {
-          while (r1 - down_seen > kMasEdge - 1) down_seen = ld_volatile_s32(&done[warp + 1]);
-        }
-        mbar_wait(&full[s], (uint32_t)((c / stages) & 1));
-        const unsigned long long sb = (unsigned long long)(slab + (size_t)r0 * T2) * 4ull;
-        const float* st = reinterpret_cast<const float*>(ring + (size_t)s * plan.stage_bytes + (sb & 15ull));
-        float a = st[ccol];
-        for (int row = r0; row < r1; ++row) {
-          const float an = (row + 1 < r1) ? st[(size_t)(row + 1 - r0) * T2 + ccol] : 0.f;
-          if (row == 0) {
-            v = (col == 0) ? a : -CUDART_INF_F;
-          } else {
-            float left = __shfl_up_sync(0xffffffffu, v, 1);
-            if (lane == 0) left = (warp == 0) ? nanv : up_edge[(row - 1) & (kMasEdge - 1)];  // NaN >= x is false
-            const bool diag = (left >= v);
-            v = __fadd_rn(a, diag ? left : v);
-            const uint32_t w = __ballot_sync(0xffffffffu, diag);
-            if (lane == 0) bits[(size_t)row * W + warp] = w;
-          }
-          if (lane == 31) my_edge[row & (kMasEdge - 1)] = v;
-          a = an;
-        }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&empty[s]);
-          __threadfence_block();
-          st_volatile_s32(&done[warp], r1);
-        }
-      }
+      if (warp == 0)
+        dp_warp<kBitsInSmem, true>(full, empty, done, edge, ring, bits_s, bits_g, plan, slab, T2, olen, nchunks, Wl,
+                                   warp, lane, b == 0);
+      else
+        dp_warp<kBitsInSmem, false>(full, empty, done, edge, ring, bits_s, bits_g, plan, slab, T2, olen, nchunks, Wl,
+                                    warp, lane, b == 0);
+      if (b == 0 && tid == 0) { g_mas_timeline[1] = gtime(); g_mas_timeline[7] = (unsigned long long)clock64(); }
     }
   } else {
     // ------------------------------ zero fill ------------------------------
     zero_fill(hard + slab, (size_t)T1 * T2, tid - (W + 1) * 32, kMasFillWarps * 32);
+    if (b == 0 && tid == (W + 1) * 32) g_mas_timeline[5] = gtime();
   }
   __syncthreads();
+  if (b == 0 && tid == 0) g_mas_timeline[2] = gtime();
 
   // ------------------------------ backtrack: 32 rows per round, bit windows in registers ------------------------------
   if (active && warp == 0) {
@@ -241,8 +338,8 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
       uint32_t win = 0;                                // bit 31 <-> column j, bit k <-> column j - 31 + k
       if (row >= 1) {
         const int wj = j >> 5;
-        const uint32_t hi = bits[(size_t)row * W + wj];
-        const uint32_t lo = wj > 0 ? bits[(size_t)row * W + wj - 1] : 0u;
+        const uint32_t hi = get_bits((size_t)row * W + wj);
+        const uint32_t lo = wj > 0 ? get_bits((size_t)row * W + wj - 1) : 0u;
         const unsigned long long x = ((unsigned long long)hi << 32) | lo;
         win = (uint32_t)(x >> ((j & 31) + 1));
       }
@@ -258,6 +355,7 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
     }
   }
   __syncthreads();
+  if (b == 0 && tid == 0) g_mas_timeline[3] = gtime();
 
   // ------------------------------ scatter ------------------------------
   if (active) {
@@ -277,6 +375,7 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
     __syncthreads();
     for (int jj = tid; jj < T2; jj += nthreads) dur[(size_t)b * T2 + jj] = dur_s[jj];
   }
+  if (b == 0 && tid == 0) g_mas_timeline[4] = gtime();
 }
 
 }  // namespace rb
@@ -321,11 +420,23 @@ extern "C" int radtts_mas_forward(const float* attn, int is_prob, const int64_t*
   uint32_t* bits_ws = plan.bits_in_smem ? nullptr : reinterpret_cast<uint32_t*>(wsp);
   static bool configured = false;
   if (!configured) {
-    RB_CUDA(cudaFuncSetAttribute(mas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    RB_CUDA(cudaFuncSetAttribute(mas_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    RB_CUDA(cudaFuncSetAttribute(mas_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     configured = true;
   }
   const unsigned long long total_bytes = (unsigned long long)B * T1 * T2 * 4ull;
-  mas_kernel<<<B, plan.threads, plan.smem_bytes, stream>>>(logp, in_lens, out_lens, T1, T2, total_bytes, attn_hard,
-                                                          frame_to_token, durations, bits_ws, plan);
+  if (plan.bits_in_smem)
+    mas_kernel<true><<<B, plan.threads, plan.smem_bytes, stream>>>(logp, in_lens, out_lens, T1, T2, total_bytes, attn_hard,
+                                                                  frame_to_token, durations, bits_ws, plan);
+  else
+    mas_kernel<false><<<B, plan.threads, plan.smem_bytes, stream>>>(logp, in_lens, out_lens, T1, T2, total_bytes, attn_hard,
+                                                                   frame_to_token, durations, bits_ws, plan);
   return after_launch();
+}
+
+extern "C" int radtts_mas_debug_timeline(unsigned long long* out8_host) {
+  if (!out8_host) return RADTTS_ERR_INVALID_ARG;
+  RB_CUDA(cudaDeviceSynchronize());
+  RB_CUDA(cudaMemcpyFromSymbol(out8_host, g_mas_timeline, 16 * sizeof(unsigned long long)));
+  return 0;
 }
