@@ -124,7 +124,9 @@ typedef struct radtts_flow_dims {
   int scaling;   /* coupling scale fn: 0 tanh, 1 exp, 2 sigmoid, 3 translate (common.py:775-787) */
 } radtts_flow_dims;
 
-/* Effective (weight-norm already applied) float32 weights in the reference's PyTorch layouts. */
+/* float32 weights in the reference's PyTorch layouts.  A weight-normed conv (torch.nn.utils.weight_norm, dim 0:
+ * w = g * v / ||v||, reference common.py:540-556) is passed either as its effective weight (wg_* = NULL) or as
+ * weight_v in w_* plus weight_g in wg_*: the prepare kernels then apply g / ||v|| while re-laying the weight out. */
 typedef struct radtts_flow_weights {
   const float* w_inv;   /* (c_active, c_active): W for forward, W^-1 for inverse */
   const float* w_start; /* (n_ch, h + n_ctx), input channel order [z0 | context] (common.py:562) */
@@ -135,6 +137,9 @@ typedef struct radtts_flow_weights {
   const float* b_rs[RADTTS_MAX_LAYERS];
   const float* w_end;   /* (2h, n_ch): rows [0,h) raw scale, [h,2h) translation */
   const float* b_end;   /* (2h) */
+  const float* wg_start;                 /* (n_ch) weight_g of `start`, or NULL */
+  const float* wg_in[RADTTS_MAX_LAYERS]; /* (n_ch) weight_g of in_layers[i], or NULL */
+  const float* wg_rs[RADTTS_MAX_LAYERS]; /* (n_ch) weight_g of res_skip_layers[i], or NULL */
 } radtts_flow_weights;
 
 /* Packed activation buffers of one flow step; caller-allocated, `rows` = radtts_frameplan_rows().
@@ -196,6 +201,21 @@ typedef struct radtts_flow_grad_buffers {
 RADTTS_API int radtts_flowstep_backward(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
                                         int Tmax, const radtts_flow_buffers* fwd, const radtts_flow_grad_buffers* g,
                                         int accumulate_ctx, int precision, void* stream);
+
+/* Weight-norm backward for the convs of one flow (what autograd derives for torch._weight_norm, reference
+ * common.py:540-556): from the effective-weight gradients radtts_flowstep_backward wrote (g_w_start, TAP-MAJOR
+ * g_w_in, g_w_rs) to the gradients of weight_v (reference layout) and weight_g:
+ *     grad_g[n] = <v_n, gw_n> / ||v_n||,   grad_v[n] = g[n]/||v_n|| * (gw_n - v_n <v_n, gw_n> / ||v_n||^2).
+ * `w` holds weight_v / weight_g as for radtts_flow_prepare; a conv with wg_* = NULL just gets its gradient copied
+ * (re-laid out) into gv_*.  accumulate != 0: += into gv_x / gg_x (gradient accumulation straight into .grad). */
+typedef struct radtts_flow_wn_grads {
+  float* gv_start; float* gg_start;                               /* (n_ch, h + n_ctx), (n_ch) */
+  float* gv_in[RADTTS_MAX_LAYERS]; float* gg_in[RADTTS_MAX_LAYERS]; /* (n_ch, n_ch, ksize), (n_ch) */
+  float* gv_rs[RADTTS_MAX_LAYERS]; float* gg_rs[RADTTS_MAX_LAYERS]; /* (n_ch, n_ch), (n_ch) */
+} radtts_flow_wn_grads;
+RADTTS_API int radtts_flow_weight_norm_backward(const radtts_flow_dims* dims, const radtts_flow_weights* w,
+                                                const radtts_flow_grad_buffers* g, const radtts_flow_wn_grads* out,
+                                                int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Kernel 3 -- ConvAttention core: pairwise L2 distance + log-softmax over text + log prior + masked softmax.

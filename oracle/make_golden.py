@@ -220,7 +220,60 @@ def gen_decoder_cfg_forward(ns):
     print("wrote decoder_cfg_forward.npz", os.path.getsize(os.path.join(GOLD, "decoder_cfg_forward.npz")), "bytes")
 
 
-GENERATORS = {"mas": gen_mas, "radtts_forward": gen_radtts_forward, "bgap": gen_bgap,
+def gen_radtts_infer(ns):
+    """RADTTS.infer (reference radtts.py:541-684), sampling direction end to end, with the noise the reference drew
+    recorded (torch.Tensor.normal_ is wrapped) so that the CUDA path can be fed the same residuals.
+      * config_ljs_radtts: B=2 ragged durations given (decoder-only model);
+      * config_ljs_bgap:   B=1, durations given, voicing / F0 / energy predicted (DAP + BGAP flows), plus the raw output
+        of the duration predictor on recorded noise (its rounding is too brittle on random weights to drive infer)."""
+    import torch
+    g = {}
+    rec = []
+    orig = torch.Tensor.normal_
+
+    def normal_rec(self, *a, **k):
+        out = orig(self, *a, **k)
+        rec.append(out.detach().clone())
+        return out
+
+    for tag, cfgname, B in (("radtts", "config_ljs_radtts.json", 2), ("bgap", "config_ljs_bgap.json", 1)):
+        model, cfg, sd = _ref_model(ns, cfgname)
+        rng = np.random.default_rng(5 + B)
+        T2 = 13
+        text = torch.from_numpy(rng.integers(1, 185, (B, T2)).astype(np.int64))
+        spk = torch.zeros(B, dtype=torch.long)
+        dur = torch.from_numpy(rng.integers(2, 7, (B, T2)).astype(np.int64))
+        for b in range(B):
+            dur[b, 0] += (4 - int(dur[b].sum()) % 4) % 4      # total frames a multiple of 4 (SURVEY Appendix A-6)
+        torch.manual_seed(77)
+        torch.Tensor.normal_ = normal_rec
+        rec.clear()
+        try:
+            with torch.no_grad():
+                out = model.infer(spk, text, 0.8, dur=dur)
+        finally:
+            torch.Tensor.normal_ = orig
+        g[tag + "_text"] = text.numpy()
+        g[tag + "_dur"] = dur.numpy()
+        g[tag + "_n_noise"] = np.array(len(rec))
+        for i, r in enumerate(rec):
+            g[tag + "_noise_%d" % i] = r.numpy()
+        for k in ("mel", "f0", "energy_avg", "voiced_mask"):
+            if out.get(k) is not None:
+                g[tag + "_" + k] = out[k].float().numpy()
+        if tag == "bgap":
+            with torch.no_grad():
+                spk_vec = model.encode_speaker(spk)
+                txt_enc, _ = model.encode_text(text, None)
+                z_dur = torch.from_numpy(rng.standard_normal((B, 1, T2), dtype=np.float32) * 0.8)
+                g["bgap_z_dur"] = z_dur.numpy()
+                g["bgap_dur_raw"] = model.dur_pred_layer.infer(z_dur, txt_enc, spk_vec).numpy()
+    np.savez_compressed(os.path.join(GOLD, "radtts_infer.npz"), **g)
+    print("wrote radtts_infer.npz", os.path.getsize(os.path.join(GOLD, "radtts_infer.npz")), "bytes;",
+          {k: v.shape for k, v in g.items() if k.endswith("mel")})
+
+
+GENERATORS = {"mas": gen_mas, "radtts_infer": gen_radtts_infer, "radtts_forward": gen_radtts_forward, "bgap": gen_bgap,
               "decoder_cfg_forward": gen_decoder_cfg_forward}
 
 if __name__ == "__main__":

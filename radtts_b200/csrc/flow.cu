@@ -129,21 +129,10 @@ __device__ __forceinline__ void put<float>(float* p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void put<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
-// conv weight (N, C, k) -> dst[n][t * C + c]  (tap-major K)
-template <typename T>
-__global__ void prep_conv_kernel(const float* __restrict__ w, int N, int C, int k, T* __restrict__ dst, int ldw) {
-  const size_t total = (size_t)N * C * k;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int t = (int)((i / C) % k);
-    const int n = (int)(i / ((size_t)C * k));
-    put(dst + (size_t)n * ldw + (size_t)t * C + c, w[((size_t)n * C + c) * k + t]);
-  }
-}
 // start weight (N, h + n_ctx) [z0 | ctx] -> dst[n][ctx (pad ctx_ld) | z0 (pad 128)]
 template <typename T>
-__global__ void prep_start_kernel(const float* __restrict__ w, int N, int h, int n_ctx, int ctx_ld,
-                                  T* __restrict__ dst) {
+__global__ void prep_start_kernel(const float* __restrict__ w, const float* __restrict__ scale, int N, int h, int n_ctx,
+                                  int ctx_ld, T* __restrict__ dst) {
   const int ldw = ctx_ld + 128;
   const size_t total = (size_t)N * ldw;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -152,8 +141,87 @@ __global__ void prep_start_kernel(const float* __restrict__ w, int N, int h, int
     float v = 0.f;
     if (j < ctx_ld) { if (j < n_ctx) v = w[(size_t)n * (h + n_ctx) + h + j]; }
     else if (j - ctx_ld < h) v = w[(size_t)n * (h + n_ctx) + (j - ctx_ld)];
-    put(dst + i, v);
+    put(dst + i, v * scale[n]);
   }
+}
+
+// ---- weight norm folded into the re-layout (torch._weight_norm, dim 0: w[n] = v[n] * g[n] / ||v[n]||) ----
+constexpr int kMaxWnItems = 1 + 2 * RADTTS_MAX_LAYERS;
+struct WnScaleParams {
+  const float* v[kMaxWnItems];
+  const float* g[kMaxWnItems];   // NULL: the tensor is an effective weight already, scale = 1
+  int ck[kMaxWnItems];           // elements per output channel
+  int n_items, nc;
+  float* scales;                 // [n_items][nc]
+};
+// one warp per (tensor, output channel)
+__global__ void __launch_bounds__(256) wn_scale_kernel(const WnScaleParams p) {
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (gw >= p.n_items * p.nc) return;
+  const int item = gw / p.nc, n = gw - item * p.nc;
+  float s = 1.f;
+  if (p.g[item]) {
+    const float* v = p.v[item] + (size_t)n * p.ck[item];
+    float acc = 0.f;
+    for (int i = lane; i < p.ck[item]; i += 32) acc = fmaf(v[i], v[i], acc);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    s = p.g[item][n] / sqrtf(acc);
+  }
+  if (lane == 0) p.scales[gw] = s;
+}
+
+// All k-tap / 1x1 convs of a WN in ONE launch: (N, C, k) fp32 -> dst[n][t * C + c] (tap-major K, scaled) and, for the
+// backward pass, the transposed copy the fused dgrad GEMMs read: dstT[c][dcolT + t * N + n].
+struct PrepConvItem {
+  const float* v;
+  const float* scale;
+  void* dst;
+  void* dstT;   // may be NULL
+  int k, lddT, dcolT, pad_;
+};
+struct PrepConvParams {
+  PrepConvItem it[2 * RADTTS_MAX_LAYERS];
+  int N, C;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) prep_convs_kernel(const PrepConvParams p) {
+  extern __shared__ float tile[];                  // [k][32][65]
+  const PrepConvItem& it = p.it[blockIdx.z];
+  const int k = it.k, N = p.N, C = p.C;
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+  const int per_row = 64 * k;
+  for (int idx = threadIdx.x; idx < 32 * per_row; idx += 256) {
+    const int n = idx / per_row, r = idx - n * per_row;
+    const int c = r / k, t = r - c * k;
+    float v = 0.f;
+    if (n0 + n < N && c0 + c < C) v = it.v[((size_t)(n0 + n) * C + c0 + c) * k + t] * it.scale[n0 + n];
+    tile[(t * 32 + n) * 65 + c] = v;
+  }
+  __syncthreads();
+  T* dst = reinterpret_cast<T*>(it.dst);
+  const size_t ldw = (size_t)k * C;
+  for (int idx = threadIdx.x; idx < k * 32 * 64; idx += 256) {
+    const int c = idx & 63, n = (idx >> 6) & 31, t = idx >> 11;
+    if (n0 + n < N && c0 + c < C) put(dst + (size_t)(n0 + n) * ldw + (size_t)t * C + c0 + c, tile[(t * 32 + n) * 65 + c]);
+  }
+  if (it.dstT) {
+    T* dstT = reinterpret_cast<T*>(it.dstT);
+    for (int idx = threadIdx.x; idx < k * 64 * 32; idx += 256) {
+      const int n = idx & 31, c = (idx >> 5) & 63, t = idx >> 11;
+      if (n0 + n < N && c0 + c < C)
+        put(dstT + (size_t)(c0 + c) * it.lddT + it.dcolT + (size_t)t * N + n0 + n, tile[(t * 32 + n) * 65 + c]);
+    }
+  }
+}
+struct CopyVecParams {
+  const float* src[kMaxWnItems];
+  float* dst[kMaxWnItems];
+  int n;
+};
+__global__ void copy_vecs_kernel(const CopyVecParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.n) p.dst[blockIdx.y][i] = p.src[blockIdx.y][i];
 }
 // end weight (2h, n_ch) -> dst[2c + p][l * n_ch + k] replicated over the n_layers K blocks; rows >= 2h zero
 template <typename T>
@@ -206,10 +274,6 @@ __global__ void prep_inv_kernel(const float* __restrict__ w, int zld, int c_off,
     if (full_t) full_t[(size_t)c * zld + r] = v;
   }
 }
-__global__ void copy_f32_kernel(const float* __restrict__ s, float* __restrict__ d, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = s[i];
-}
-
 // inverse direction prologue: z0 copy for `start`, and zmid[:, < c_off + h] = zin
 template <typename T>
 __global__ void extract_z0_kernel(const float* __restrict__ zin, int zld, int c_off, int h, const int* __restrict__ plan,
@@ -237,21 +301,60 @@ static int prepare_impl(const radtts_flow_dims& d, const radtts_flow_weights& w,
   float* invt = want_backward ? reinterpret_cast<float*>(base + L.w_inv_t) : nullptr;
   prep_inv_kernel<<<grid_for((size_t)d.z_ld * d.z_ld), 256, 0, st>>>(w.w_inv, d.z_ld, d.c_off, invf, invt);
   RB_TRY(after_launch());
+  // weight-norm scales g / ||v|| of every conv (1 where the caller passed an effective weight)
+  float* scales = reinterpret_cast<float*>(base + L.scales);
+  {
+    WnScaleParams sp{};
+    sp.n_items = 1 + 2 * nl;
+    sp.nc = nc;
+    sp.scales = scales;
+    sp.v[0] = w.w_start; sp.g[0] = w.wg_start; sp.ck[0] = h + d.n_ctx;
+    for (int i = 0; i < nl; ++i) {
+      sp.v[1 + i] = w.w_in[i]; sp.g[1 + i] = w.wg_in[i]; sp.ck[1 + i] = nc * k;
+      sp.v[1 + nl + i] = w.w_rs[i]; sp.g[1 + nl + i] = w.wg_rs[i]; sp.ck[1 + nl + i] = nc;
+    }
+    wn_scale_kernel<<<ceil_div(sp.n_items * nc, 8), 256, 0, st>>>(sp);
+    RB_TRY(after_launch());
+  }
   T* ws = reinterpret_cast<T*>(base + L.w_start);
-  prep_start_kernel<T><<<grid_for((size_t)nc * ldstart), 256, 0, st>>>(w.w_start, nc, h, d.n_ctx, L.ctx_ld, ws);
+  prep_start_kernel<T><<<grid_for((size_t)nc * ldstart), 256, 0, st>>>(w.w_start, scales, nc, h, d.n_ctx, L.ctx_ld, ws);
   RB_TRY(after_launch());
-  copy_f32_kernel<<<grid_for(nc), 256, 0, st>>>(w.b_start, reinterpret_cast<float*>(base + L.b_start), nc);
-  RB_TRY(after_launch());
-  for (int i = 0; i < nl; ++i) {
-    prep_conv_kernel<T><<<grid_for((size_t)nc * nc * k), 256, 0, st>>>(w.w_in[i], nc, nc, k,
-                                                                      reinterpret_cast<T*>(base + L.w_in[i]), k * nc);
+  {
+    CopyVecParams cp{};
+    cp.n = nc;
+    cp.src[0] = w.b_start; cp.dst[0] = reinterpret_cast<float*>(base + L.b_start);
+    for (int i = 0; i < nl; ++i) {
+      cp.src[1 + i] = w.b_in[i]; cp.dst[1 + i] = reinterpret_cast<float*>(base + L.b_in[i]);
+      cp.src[1 + nl + i] = w.b_rs[i]; cp.dst[1 + nl + i] = reinterpret_cast<float*>(base + L.b_rs[i]);
+    }
+    copy_vecs_kernel<<<dim3(ceil_div(nc, 256), 1 + 2 * nl), 256, 0, st>>>(cp);
     RB_TRY(after_launch());
-    prep_conv_kernel<T><<<grid_for((size_t)nc * nc), 256, 0, st>>>(w.w_rs[i], nc, nc, 1,
-                                                                  reinterpret_cast<T*>(base + L.w_rs[i]), nc);
+  }
+  {
+    // in_layers and res_skip layers, forward layout + (want_backward) the dgrad layout, one launch:
+    //   dgrad GEMM of layer i reads [ rs_i^T | in_{i+1}^T taps ] (w_dg[i]); the first conv's transpose is w_dg0
+    PrepConvParams pp{};
+    pp.N = nc; pp.C = nc;
+    for (int i = 0; i < nl; ++i) {
+      PrepConvItem& a = pp.it[i];
+      a.v = w.w_in[i]; a.scale = scales + (size_t)(1 + i) * nc; a.dst = base + L.w_in[i]; a.k = k;
+      if (want_backward) {
+        if (i == 0) { a.dstT = base + L.w_dg0; a.lddT = k * nc; a.dcolT = 0; }
+        else { a.dstT = base + L.w_dg[i - 1]; a.lddT = L.dg_k[i - 1]; a.dcolT = nc; }
+      }
+      PrepConvItem& r = pp.it[nl + i];
+      r.v = w.w_rs[i]; r.scale = scales + (size_t)(1 + nl + i) * nc; r.dst = base + L.w_rs[i]; r.k = 1;
+      if (want_backward) { r.dstT = base + L.w_dg[i]; r.lddT = L.dg_k[i]; r.dcolT = 0; }
+    }
+    // two launches (k taps / 1 tap) so that the 1x1 items do not pay for the k-tap tile
+    const size_t smem_k = (size_t)k * 32 * 65 * sizeof(float), smem_1 = (size_t)32 * 65 * sizeof(float);
+    if (smem_k > 48 * 1024) return RADTTS_ERR_UNSUPPORTED;
+    prep_convs_kernel<T><<<dim3(ceil_div(nc, 32), ceil_div(nc, 64), nl), 256, smem_k, st>>>(pp);
     RB_TRY(after_launch());
-    copy_f32_kernel<<<grid_for(nc), 256, 0, st>>>(w.b_in[i], reinterpret_cast<float*>(base + L.b_in[i]), nc);
-    RB_TRY(after_launch());
-    copy_f32_kernel<<<grid_for(nc), 256, 0, st>>>(w.b_rs[i], reinterpret_cast<float*>(base + L.b_rs[i]), nc);
+    PrepConvParams pr{};
+    pr.N = nc; pr.C = nc;
+    for (int i = 0; i < nl; ++i) pr.it[i] = pp.it[nl + i];
+    prep_convs_kernel<T><<<dim3(ceil_div(nc, 32), ceil_div(nc, 64), nl), 256, smem_1, st>>>(pr);
     RB_TRY(after_launch());
   }
   prep_end_kernel<T><<<grid_for((size_t)d.z_ld * nl * nc), 256, 0, st>>>(
@@ -270,14 +373,6 @@ static int prepare_impl(const radtts_flow_dims& d, const radtts_flow_weights& w,
                                                                         (size_t)nc * L.end_kpad);
   RB_TRY(after_launch());
   RB_TRY(transpose(L.w_end, nl * nc, 0, d.z_ld, nc, L.w_end_t, L.end_kpad, 0));
-  // fused dgrad weights: layer i: [ rs_i^T | in_{i+1}^T taps ]
-  for (int i = 0; i < nl; ++i) {
-    const int ldd = L.dg_k[i];
-    RB_TRY(transpose(L.w_rs[i], nc, 0, nc, nc, L.w_dg[i], ldd, 0));
-    if (i + 1 < nl)
-      for (int t = 0; t < k; ++t) RB_TRY(transpose(L.w_in[i + 1], k * nc, t * nc, nc, nc, L.w_dg[i], ldd, nc + t * nc));
-  }
-  for (int t = 0; t < k; ++t) RB_TRY(transpose(L.w_in[0], k * nc, t * nc, nc, nc, L.w_dg0, k * nc, t * nc));
   RB_TRY(transpose(L.w_start, ldstart, 0, nc, ldstart, L.w_start_t, nc, 0));
   return 0;
 }

@@ -242,6 +242,71 @@ static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const P
   return 0;
 }
 
+// ----------------------------------------------------------------------------------------------------
+// 7. weight-norm backward, all convs of the flow in one launch (replaces 9 torch._weight_norm_interface_backward
+//    launches + the tap-major -> (n, c, k) permute copies).  One CTA per (tensor, output channel).
+// ----------------------------------------------------------------------------------------------------
+constexpr int kWnMaxItems = 1 + 2 * RADTTS_MAX_LAYERS;
+struct WnBwdItem {
+  const float* v;    // weight_v (N, C, k) -- or the effective weight when g == NULL
+  const float* g;    // weight_g (N) or NULL
+  const float* gw;   // gradient of the effective weight: tap_major ? [k][N][C] : [N][C * k]
+  float* gv;         // out (N, C, k)
+  float* gg;         // out (N), unused when g == NULL
+  int C, k, tap_major, pad_;
+};
+struct WnBwdParams {
+  WnBwdItem it[kWnMaxItems];
+  int N, accumulate;
+};
+__global__ void __launch_bounds__(256) wn_bwd_kernel(const WnBwdParams p) {
+  extern __shared__ float gws[];                 // the channel's gradient row in (c, t) order
+  __shared__ float red[2][8];
+  const WnBwdItem& it = p.it[blockIdx.y];
+  const int n = blockIdx.x, N = p.N, C = it.C, k = it.k, CK = C * k;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (it.tap_major) {
+    for (int t = 0; t < k; ++t)
+      for (int c = tid; c < C; c += 256) gws[c * k + t] = it.gw[((size_t)t * N + n) * C + c];
+  } else {
+    for (int i = tid; i < CK; i += 256) gws[i] = it.gw[(size_t)n * CK + i];
+  }
+  __syncthreads();
+  float* gv = it.gv + (size_t)n * CK;
+  if (!it.g) {                                   // not weight-normed: gradient of the weight itself
+    for (int i = tid; i < CK; i += 256) gv[i] = p.accumulate ? gv[i] + gws[i] : gws[i];
+    return;
+  }
+  const float* v = it.v + (size_t)n * CK;
+  float dot = 0.f, nrm2 = 0.f;
+  for (int i = tid; i < CK; i += 256) {
+    const float x = v[i];
+    dot = fmaf(x, gws[i], dot);
+    nrm2 = fmaf(x, x, nrm2);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
+  }
+  if (lane == 0) { red[0][warp] = dot; red[1][warp] = nrm2; }
+  __syncthreads();
+  dot = 0.f; nrm2 = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { dot += red[0][w]; nrm2 += red[1][w]; }
+  const float norm = sqrtf(nrm2);
+  const float scale = it.g[n] / norm;            // w = v * scale
+  const float proj = dot / nrm2;
+  for (int i = tid; i < CK; i += 256) {
+    const float val = scale * (gws[i] - v[i] * proj);
+    gv[i] = p.accumulate ? gv[i] + val : val;
+  }
+  if (tid == 0) {
+    const float val = dot / norm;
+    it.gg[n] = p.accumulate ? it.gg[n] + val : val;
+  }
+}
+
 }  // namespace rb
 
 using namespace rb;
@@ -264,4 +329,31 @@ extern "C" int radtts_flowstep_backward(const radtts_flow_dims* dims, const void
   if (precision == RADTTS_PREC_BF16)
     return backward_impl<__nv_bfloat16>(*dims, base, pv, *fwd, *g, accumulate_ctx, (cudaStream_t)stream);
   return RADTTS_ERR_INVALID_ARG;
+}
+
+extern "C" int radtts_flow_weight_norm_backward(const radtts_flow_dims* dims, const radtts_flow_weights* w,
+                                                const radtts_flow_grad_buffers* g, const radtts_flow_wn_grads* out,
+                                                int accumulate, void* stream) {
+  RB_TRY(check_dims(dims));
+  if (!w || !g || !out) return RADTTS_ERR_INVALID_ARG;
+  const int nl = dims->n_layers, nc = dims->n_ch, k = dims->ksize, h = dims->c_active / 2;
+  WnBwdParams p{};
+  p.N = nc;
+  p.accumulate = accumulate ? 1 : 0;
+  auto set = [&](int idx, const float* v, const float* wg, const float* gw, float* gv, float* gg, int C, int kk,
+                 int tap_major) -> int {
+    if (!v || !gw || !gv || (wg && !gg)) return RADTTS_ERR_INVALID_ARG;
+    p.it[idx] = WnBwdItem{v, wg, gw, gv, gg, C, kk, tap_major, 0};
+    return 0;
+  };
+  RB_TRY(set(0, w->w_start, w->wg_start, g->g_w_start, out->gv_start, out->gg_start, h + dims->n_ctx, 1, 0));
+  for (int i = 0; i < nl; ++i) {
+    RB_TRY(set(1 + i, w->w_in[i], w->wg_in[i], g->g_w_in[i], out->gv_in[i], out->gg_in[i], nc, k, 1));
+    RB_TRY(set(1 + nl + i, w->w_rs[i], w->wg_rs[i], g->g_w_rs[i], out->gv_rs[i], out->gg_rs[i], nc, 1, 0));
+  }
+  const int maxck = nc * k > h + dims->n_ctx ? nc * k : h + dims->n_ctx;
+  const size_t smem = (size_t)maxck * sizeof(float);
+  if (smem > 48 * 1024) return RADTTS_ERR_UNSUPPORTED;
+  wn_bwd_kernel<<<dim3(nc, 1 + 2 * nl), 256, smem, (cudaStream_t)stream>>>(p);
+  return after_launch();
 }

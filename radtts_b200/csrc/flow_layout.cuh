@@ -10,6 +10,7 @@ struct FlowLayout {
   int end_kpad;   // K of the `end` dgrad GEMM: round_up(z_ld, 64)
   size_t w_inv, w_start, b_start, w_in[RADTTS_MAX_LAYERS], b_in[RADTTS_MAX_LAYERS], w_rs[RADTTS_MAX_LAYERS],
       b_rs[RADTTS_MAX_LAYERS], w_end, b_end;
+  size_t scales;  // float [(1 + 2 n_layers)][n_ch]: g / ||v|| of start, in_layers, res_skip_layers (1 where not weight-normed)
   // backward section
   size_t w_inv_t, w_end_t, w_dg[RADTTS_MAX_LAYERS], w_dg0, w_start_t;
   int dg_k[RADTTS_MAX_LAYERS];
@@ -35,6 +36,7 @@ inline FlowLayout flow_layout(const radtts_flow_dims& d, int precision, int want
   }
   L.w_end = take((size_t)d.z_ld * nl * nc * es);
   L.b_end = take((size_t)d.z_ld * 4);
+  L.scales = take((1 + 2 * nl) * nc * 4);
   L.fwd_total = off;
   if (want_backward) {
     L.w_inv_t = take((size_t)d.z_ld * d.z_ld * 4);

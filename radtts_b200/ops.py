@@ -17,6 +17,18 @@ _SCALING = {"tanh": 0, "exp": 1, "sigmoid": 2, "translate": 3}
 _forced_precision = None
 
 
+_direct_grad = False
+
+
+def set_direct_grad_accumulation(on):
+    """on: the flow stack's backward adds the weight_v / weight_g gradients directly into the parameters' .grad
+    tensors (when they exist, are fp32 and contiguous) and returns no gradient for them to autograd.  Equivalent to
+    what AccumulateGrad would do, minus one elementwise launch per parameter; hooks on those parameters (DDP) do not
+    fire, so only trainers that reduce gradients themselves (radtts_b200.trainer) switch it on."""
+    global _direct_grad
+    _direct_grad = bool(on)
+
+
 def set_precision(p):
     """None: follow torch autocast (bf16 inside autocast, fp32 otherwise); 'fp32' / 'bf16': force."""
     global _forced_precision
@@ -47,7 +59,13 @@ _P = ctypes.c_void_p
 
 class FlowWeights(ctypes.Structure):
     _fields_ = [("w_inv", _P), ("w_start", _P), ("b_start", _P), ("w_in", _P * MAX_LAYERS), ("b_in", _P * MAX_LAYERS),
-                ("w_rs", _P * MAX_LAYERS), ("b_rs", _P * MAX_LAYERS), ("w_end", _P), ("b_end", _P)]
+                ("w_rs", _P * MAX_LAYERS), ("b_rs", _P * MAX_LAYERS), ("w_end", _P), ("b_end", _P),
+                ("wg_start", _P), ("wg_in", _P * MAX_LAYERS), ("wg_rs", _P * MAX_LAYERS)]
+
+
+class FlowWnGrads(ctypes.Structure):
+    _fields_ = [("gv_start", _P), ("gg_start", _P), ("gv_in", _P * MAX_LAYERS), ("gg_in", _P * MAX_LAYERS),
+                ("gv_rs", _P * MAX_LAYERS), ("gg_rs", _P * MAX_LAYERS)]
 
 
 class FlowBuffers(ctypes.Structure):
@@ -194,32 +212,57 @@ def _flow_dims(flow, z_ld, c_active):
                     scaling=_SCALING[scaling])
 
 
+def _v_and_g(conv):
+    """(weight or weight_v, weight_g or None) of a possibly weight-normed conv (torch.nn.utils.weight_norm, dim 0):
+    the library applies g / ||v|| itself while re-laying the weight out, and derives both gradients."""
+    if hasattr(conv, "weight_v"):
+        return conv.weight_v, conv.weight_g
+    return conv.weight, None
+
+
 def _flow_weight_list(flow, inverse):
-    """Flat list of effective fp32 weights, in the order FlowWeights expects."""
+    """Flat list of fp32 weight tensors in the order FlowWeights expects (3 + 4 n_layers + 2 entries: weight_v where a
+    conv is weight-normed), followed by the 1 + 2 n_layers weight_g tensors (None where it is not)."""
     wn = flow.affine_tfn.affine_param_predictor
     inv = flow.invtbl_conv
     if hasattr(inv, "lower"):
         w_inv = inv.inverse_weight() if inverse else inv.weight()
     else:
         w_inv = inv.inverse_weight() if inverse else inv.conv.weight.squeeze(-1)
-    ws = [w_inv.float(), _effective(wn.start).squeeze(-1), wn.start.bias]
+    v_start, g_start = _v_and_g(wn.start)
+    ws = [w_inv.float(), v_start, wn.start.bias]
+    gs = [g_start]
     for i in range(wn.n_layers):
-        ws += [_effective(wn.in_layers[i].conv), wn.in_layers[i].conv.bias]
+        v, g = _v_and_g(wn.in_layers[i].conv)
+        ws += [v, wn.in_layers[i].conv.bias]
+        gs.append(g)
+    g_rs = []
     for i in range(wn.n_layers):
-        ws += [_effective(wn.res_skip_layers[i]).squeeze(-1), wn.res_skip_layers[i].bias]
-    ws += [wn.end.weight.squeeze(-1), wn.end.bias]
-    return ws
+        v, g = _v_and_g(wn.res_skip_layers[i])
+        ws += [v, wn.res_skip_layers[i].bias]
+        g_rs.append(g)
+    ws += [wn.end.weight, wn.end.bias]
+    return ws + gs + g_rs
+
+
+def n_weight_tensors(n_layers):
+    return 3 + 4 * n_layers + 2
 
 
 def _weights_struct(ws, n_layers):
-    ws = [w.detach().float().contiguous() for w in ws]
+    ws = [None if w is None else w.detach().float().contiguous() for w in ws]
     s = FlowWeights()
     s.w_inv, s.w_start, s.b_start = _p(ws[0]), _p(ws[1]), _p(ws[2])
     for i in range(n_layers):
         s.w_in[i], s.b_in[i] = _p(ws[3 + 2 * i]), _p(ws[4 + 2 * i])
         s.w_rs[i], s.b_rs[i] = _p(ws[3 + 2 * n_layers + 2 * i]), _p(ws[4 + 2 * n_layers + 2 * i])
     s.w_end, s.b_end = _p(ws[3 + 4 * n_layers]), _p(ws[4 + 4 * n_layers])
-    return s, ws  # keep `ws` alive until the prepare kernels have been enqueued on the stream
+    nw = n_weight_tensors(n_layers)
+    s.wg_start = _p(ws[nw])
+    for i in range(n_layers):
+        s.wg_in[i] = _p(ws[nw + 1 + i])
+        s.wg_rs[i] = _p(ws[nw + 1 + n_layers + i])
+    return s, ws  # keep `ws` alive until the kernels have been enqueued on the stream
 
 
 def prepare_flow(dims, ws, prec, want_backward, device):
@@ -315,11 +358,12 @@ def run_flowstep(dims, blob, plan, zin, ctx_packed, prec, inverse, lease, keep_p
 
 class _FlowStackFn(torch.autograd.Function):
     """A run of consecutive decoder flows on packed rows (the whole 8-flow stack in RADTTS.forward, a single flow
-    for FlowStep.forward).  Inputs: zin [rows][z_ld] fp32, ctx [rows][ctx_ld] act, then the effective weights of
-    every flow (weight-norm / LUS parameter gradients are left to autograd).  Returns (zout, log_s_0, ...)."""
+    for FlowStep.forward).  Inputs: zin [rows][z_ld] fp32, ctx [rows][ctx_ld] act, then the weight tensors of
+    every flow as _flow_weight_list orders them (weight_v / weight_g go in as they are: weight norm and its backward run
+    inside the library; the LUS composition of the 1x1 matrix is left to autograd).  Returns (zout, log_s_0, ...)."""
 
     @staticmethod
-    def forward(ctx, zin, ctx_packed, plan, dims_list, prec, inverse, n_per_flow, *ws):
+    def forward(ctx, zin, ctx_packed, plan, dims_list, prec, inverse, n_per_flow, sinks, *ws):
         need_bwd = (not inverse) and any(ctx.needs_input_grad)
         order = range(len(dims_list))
         if inverse:
@@ -336,13 +380,15 @@ class _FlowStackFn(torch.autograd.Function):
             lease = _Lease()
             zout, log_s, bufs, _ = run_flowstep(dims, blob, plan, z, ctx_packed, prec, inverse, lease, need_bwd)
             if need_bwd:
-                saved[i] = (blob, bufs, lease)
+                saved[i] = (blob, bufs, lease, ws[i * n_per_flow:(i + 1) * n_per_flow],
+                            None if sinks is None else sinks[i * n_per_flow:(i + 1) * n_per_flow])
             else:
                 lease.release()
             log_s_all[i] = log_s
             z = zout
         if need_bwd:
-            ctx.saved = (plan, dims_list, prec, n_per_flow, saved, [tuple(w.shape) for w in ws], ctx_packed.dtype)
+            ctx.saved = (plan, dims_list, prec, n_per_flow, saved,
+                         [None if w is None else tuple(w.shape) for w in ws], ctx_packed.dtype)
         if inverse:
             return z
         return (z,) + tuple(log_s_all)
@@ -380,13 +426,17 @@ def flow_stack_packed(flows, zin, ctx_packed, plan, z_ld, actives, inverse=False
         # inference: weights are frozen between calls -> the re-laid-out blobs are cached per flow (keyed on the
         # parameters' version counters), and neither weight norm nor W^-1 nor the re-layout run again
         blobs = [_cached_blob(f, d, prec, inverse, zin.device) for f, d in zip(flows, dims_list)]
-        out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, 0, *blobs)
+        out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, 0, None, *blobs)
     else:
         ws = []
         for f in flows:
             ws += _flow_weight_list(f, inverse)
         n_per = len(ws) // len(flows)
-        out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, n_per, *ws)
+        # gradient sinks: with direct accumulation on, the weight-norm backward kernel adds grad_v / grad_g straight
+        # into the parameters' existing .grad (e.g. views of the optimizer's flat buffer) instead of handing 144 tensors
+        # to autograd's AccumulateGrad
+        sinks = [w if (_direct_grad and isinstance(w, torch.nn.Parameter)) else None for w in ws] if _direct_grad else None
+        out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, n_per, sinks, *ws)
     if inverse:
         return out
     zout, log_s = out[0], list(out[1:])

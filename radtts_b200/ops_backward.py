@@ -22,7 +22,7 @@ def flow_stack_backward(saved, g_zout, g_log_s):
     first = True
     for i in reversed(range(len(dims_list))):
         dims = dims_list[i]
-        blob, bufs, lease = saved_list[i]
+        blob, bufs, lease, ws, sinks = saved_list[i]
         nl, nc, k = dims.n_layers, dims.n_ch, dims.ksize
         h = dims.c_active // 2
         gl = g_log_s[i] if i < len(g_log_s) else None
@@ -63,15 +63,50 @@ def flow_stack_backward(saved, g_zout, g_log_s):
         lease.release()
         saved_list[i] = None
         base = i * n_per
-        out = [gw_inv_full[dims.c_off:, dims.c_off:], gw_start, gb_start]
+        nw = ops.n_weight_tensors(nl)
+        # weight-norm backward (and the tap-major -> (out, in, tap) re-layout of the in_layer gradients), one launch
+        wstruct, keep = ops._weights_struct(ws, nl)
+        idx_v = [1] + [3 + 2 * j for j in range(nl)] + [3 + 2 * nl + 2 * j for j in range(nl)]
+        idx_g = [nw] + [nw + 1 + j for j in range(nl)] + [nw + 1 + nl + j for j in range(nl)]
+
+        def sink_ok(j):
+            t = None if sinks is None else sinks[j]
+            if ws[j] is None:
+                return True        # nothing to write for an absent weight_g
+            gr = None if t is None else t.grad
+            return gr is not None and gr.dtype == torch.float32 and gr.is_contiguous() and gr.shape == t.shape
+
+        direct = sinks is not None and all(sink_ok(j) for j in idx_v + idx_g)
+        outs = {}
+        for j in idx_v + idx_g:
+            if ws[j] is None:
+                outs[j] = None
+            elif direct:
+                outs[j] = sinks[j].grad
+            else:
+                outs[j] = torch.empty(w_shapes[base + j], dtype=torch.float32, device=dev)
+        wg = ops.FlowWnGrads(gv_start=ops._p(outs[idx_v[0]]), gg_start=ops._p(outs[idx_g[0]]))
         for j in range(nl):
-            out += [gw_in[j].permute(1, 2, 0), gb_in[j]]
+            wg.gv_in[j], wg.gg_in[j] = ops._p(outs[idx_v[1 + j]]), ops._p(outs[idx_g[1 + j]])
+            wg.gv_rs[j], wg.gg_rs[j] = ops._p(outs[idx_v[1 + nl + j]]), ops._p(outs[idx_g[1 + nl + j]])
+        _lib.check(L.radtts_flow_weight_norm_backward(ctypes.byref(dims), ctypes.byref(wstruct), ctypes.byref(g),
+                                                      ctypes.byref(wg), 1 if direct else 0, stream),
+                   "radtts_flow_weight_norm_backward")
+        out = [None] * n_per
+        out[0] = gw_inv_full[dims.c_off:, dims.c_off:]
+        out[2] = gb_start
         for j in range(nl):
-            out += [gw_rs[j], gb_rs[j]]
-        out += [gw_end, gb_end]
+            out[4 + 2 * j] = gb_in[j]
+            out[4 + 2 * nl + 2 * j] = gb_rs[j]
+        out[3 + 4 * nl] = gw_end
+        out[4 + 4 * nl] = gb_end
+        if not direct:
+            for j in idx_v + idx_g:
+                out[j] = outs[j]
         for j, t in enumerate(out):
-            assert tuple(t.shape) == tuple(w_shapes[base + j]), (j, t.shape, w_shapes[base + j])
-            grads[base + j] = t
+            if t is not None:
+                assert t.numel() == int(torch.Size(w_shapes[base + j]).numel()), (j, t.shape, w_shapes[base + j])
+                grads[base + j] = t.reshape(w_shapes[base + j])
         g_z = g_zin
     g_ctx_out = g_ctx if ctx_dtype == torch.float32 else g_ctx.to(ctx_dtype)
-    return (g_z, g_ctx_out, None, None, None, None, None) + tuple(grads)
+    return (g_z, g_ctx_out, None, None, None, None, None, None) + tuple(grads)

@@ -14,6 +14,12 @@ from .common import (AffineTransformationLayer, ConvAttention, Encoder, Exponent
                      run_bilstm)
 
 
+def _noise(shape, device):
+    """Standard-normal draw for RADTTS.infer (reference radtts.py:559,607,622,652 use torch.cuda.FloatTensor.normal_);
+    a module-level function so that parity tests can substitute the reference's recorded noise."""
+    return torch.randn(*shape, device=device)
+
+
 class FlowStep(nn.Module):
     """One decoder flow: invertible 1x1 conv then affine coupling (reference radtts.py:31-59)."""
 
@@ -307,7 +313,7 @@ class RADTTS(nn.Module):
         txt_enc, _ = self.encode_text(text, None)
 
         if dur is None:
-            z_dur = torch.randn(batch_size, 1, n_tokens, device=dev) * sigma_dur
+            z_dur = _noise((batch_size, 1, n_tokens), dev) * sigma_dur
             dur = self.dur_pred_layer.infer(z_dur, txt_enc, spk_vec_text)
             if dur.shape[-1] < txt_enc.shape[-1]:
                 dur = nn.functional.pad(dur, (0, txt_enc.shape[-1] - dur.shape[2]), mode="replicate")
@@ -333,7 +339,7 @@ class RADTTS(nn.Module):
                 f0_bias = f0_bias * (~voiced_mask.bool()).float()
             if f0 is None:
                 n_ch = 2 if self.use_first_order_features else 1
-                z_f0 = torch.randn(batch_size, n_ch, max_n_frames, device=dev) * sigma_f0
+                z_f0 = _noise((batch_size, n_ch, max_n_frames), dev) * sigma_f0
                 f0 = self.infer_f0(z_f0, ap_txt, spk_vec_attributes, voiced_mask, out_lens)[:, 0]
             if f0_mean > 0.0:
                 vb = voiced_mask.bool()
@@ -342,7 +348,7 @@ class RADTTS(nn.Module):
                 f0[vb] = f0[vb] * (f0_std if f0_std > 0 else sd) + f0_mean
             if energy_avg is None:
                 n_ch = 2 if self.use_first_order_features else 1
-                z_e = torch.randn(batch_size, n_ch, max_n_frames, device=dev) * sigma_energy
+                z_e = _noise((batch_size, n_ch, max_n_frames), dev) * sigma_energy
                 energy_avg = self.infer_energy(z_e, ap_txt, spk_vec, out_lens)[:, 0]
             n0 = int(out_lens[0])
             if energy_avg.shape[1] < n0:  # reference radtts.py:629-637 (both padded by the energy deficit)
@@ -357,8 +363,7 @@ class RADTTS(nn.Module):
         else:
             context_w_spkvec = self.preprocess_context(txt_enc_time_expanded, spk_vec, out_lens, None, None)
 
-        residual = torch.randn(batch_size, 80 * self.n_group_size, max_n_frames // self.n_group_size,
-                               device=dev) * sigma
+        residual = _noise((batch_size, 80 * self.n_group_size, max_n_frames // self.n_group_size), dev) * sigma
         mel = ops.decoder_inverse(self, residual, context_w_spkvec, out_lens)
         if self.do_mel_descaling:
             mel = mel * 2 - 5.5

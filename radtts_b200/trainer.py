@@ -34,8 +34,12 @@ class TrainStep:
         self.capturable = bool(capturable)
         self.fused_optimizer = bool(fused_optimizer)
         if self.fused_optimizer:
+            from . import ops
             from .optim import FusedRAdam
             self.optimizer = FusedRAdam(params, lr=lr, weight_decay=weight_decay)
+            # gradients live in the optimizer's flat buffer and this class reduces them itself (no DDP hooks): let
+            # the flow stack's backward add weight_v / weight_g gradients straight into it
+            ops.set_direct_grad_accumulation(True)
         else:
             self.optimizer = torch.optim.RAdam(params, lr=lr, weight_decay=weight_decay, foreach=True,
                                                capturable=self.capturable)
