@@ -271,14 +271,16 @@ RADTTS_API int radtts_pointwise_conv_small(const float* x, const float* w, int B
  *   gates_save (2, T, B, 4H), c_save (2, T, B, H): activations saved for backward (NULL for inference);
  *   backward: dh_all (T, B, 2H) -> dgates_all (2, T, B, 4H) (pre-activation gate gradients).
  *   B <= 32, H <= 592.  ws: radtts_lstm_workspace_bytes(B, H).
+ *   precision: RADTTS_PREC_FP32 -- fp32 FMA recurrence; RADTTS_PREC_BF16 (H % 8 == 0, else fp32) -- the recurrent product runs
+ *   on tensor cores with bf16 W_hh and bf16 exchanged h / dgates, fp32 accumulate; state, gates and every output fp32.
  * ---------------------------------------------------------------------------------------------- */
 RADTTS_API size_t radtts_lstm_workspace_bytes(int B, int H);
 RADTTS_API int radtts_lstm_forward(const float* gx, const float* whh, const int* lens, int T, int B, int H,
                                    float* h_all, float* gates_save, float* c_save, void* ws, size_t ws_bytes,
-                                   void* stream);
+                                   int precision, void* stream);
 RADTTS_API int radtts_lstm_backward(const float* dh_all, const float* whh, const int* lens, const float* gates_save,
                                     const float* c_save, int T, int B, int H, float* dgates_all, void* ws,
-                                    size_t ws_bytes, void* stream);
+                                    size_t ws_bytes, int precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Attention CTC loss, fused.  Replaces AttentionCTCLoss.forward (reference loss.py:118-135): blank

@@ -11,6 +11,8 @@
 //
 // fp32 throughout (state, weights, accumulation).  Gate order i, f, g, o as in torch.nn.LSTM.
 #include "common.cuh"
+#include <cuda_bf16.h>
+
 #include "ptx.cuh"
 
 namespace rb {
@@ -334,6 +336,280 @@ lstm_bwd_kernel(const float* __restrict__ dh_all, const float* __restrict__ whh,
   }
 }
 
+// ==========================================================================================================
+// bf16 tensor-core variants (precision = RADTTS_PREC_BF16, i.e. under autocast -- where cuDNN would run the whole LSTM
+// in half precision).  Only the recurrent product uses bf16 operands (W_hh and the exchanged h_{t-1} / dgates_{t+1});
+// accumulation, gates, cell state, outputs and saved tensors stay fp32.
+//   * the per-step GEMM of a CTA is tiny (32 gate rows x 32 batch x H): mma.sync.m16n8k16 with the operands laid out
+//     in shared memory in FRAGMENT ORDER, so a thread fetches its A fragment with one LDS.128 and its B fragment with
+//     one LDS.64, conflict-free; the SIMT version spent ~3 us per step on FMAs + a 16-way smem reduction;
+//   * the exchange buffers live in global memory in that same fragment order, in bf16: half the bytes per step
+//     (fwd 32 KB, bwd 128 KB per CTA) and one bulk async copy lands them ready to use.
+// U = 8 units per CTA (one m16n8 C fragment row <-> one unit), H % 8 == 0 (K is zero-padded to a multiple of 16).
+// ==========================================================================================================
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint4& a, const uint2& b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y));
+}
+
+constexpr int kLstmMmaFwdThreads = 128;   // 4 warps = 4 batch n-tiles of 8; each warp: 2 m-tiles x full K
+
+// hbuf (bf16, fragment order): [2 dir][2 ping-pong][KS = H/16][4 n-tiles][32 lanes] uint2
+__global__ void __launch_bounds__(kLstmMmaFwdThreads, 1)
+lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whh, const int* __restrict__ lens, LstmDims d,
+                    float* __restrict__ h_all, float* __restrict__ gates_save, float* __restrict__ c_save,
+                    uint2* __restrict__ hbuf, unsigned* __restrict__ counters) {
+  extern __shared__ __align__(128) uint8_t smraw[];
+  const int T = d.T, B = d.B, H = d.H;
+  const int KS = (H + 15) / 16;              // K = H padded to 16 with zero weights / zero state
+  const int dir = blockIdx.x / d.G, cta = blockIdx.x % d.G;
+  const int u0 = cta * 8;
+  uint4* ws = reinterpret_cast<uint4*>(smraw);                       // [2 m-tiles][KS][32]
+  uint2* hs = reinterpret_cast<uint2*>(smraw + (size_t)2 * KS * 32 * sizeof(uint4));   // [KS][4][32]
+  __shared__ __align__(8) uint64_t bar[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+  // W slice in A-fragment order.  m-tile 0: rows 0-7 gate i, 8-15 gate f; m-tile 1: gate g, gate o (unit = row & 7)
+  const float* W = whh + (size_t)dir * 4 * H * H;
+  for (int i = tid; i < 2 * KS * 32; i += kLstmMmaFwdThreads) {
+    const int ln = i & 31, ks = (i >> 5) % KS, mt = i / (32 * KS);
+    const int gg = ln >> 2, qq = ln & 3;
+    const int k = ks * 16 + 2 * qq;
+    const float* r0 = W + (size_t)((2 * mt) * H + u0 + gg) * H;       // row gg   (gate 2 mt)
+    const float* r1 = W + (size_t)((2 * mt + 1) * H + u0 + gg) * H;   // row gg+8 (gate 2 mt + 1)
+    auto at = [&](const float* r, int kk) { return kk < H ? r[kk] : 0.f; };
+    ws[i] = make_uint4(pack_bf16(at(r0, k), at(r0, k + 1)), pack_bf16(at(r1, k), at(r1, k + 1)),
+                       pack_bf16(at(r0, k + 8), at(r0, k + 9)), pack_bf16(at(r1, k + 8), at(r1, k + 9)));
+  }
+  const int u = u0 + g;                       // the unit this thread finalises, for batch columns bcol, bcol + 1
+  const int bcol = warp * 8 + 2 * q;
+  int len_b[2];
+  len_b[0] = bcol < B ? lens[bcol] : 0;
+  len_b[1] = bcol + 1 < B ? lens[bcol + 1] : 0;
+  float c_state[2] = {0.f, 0.f};
+  unsigned phase = 0;
+  const size_t hbytes = (size_t)KS * 4 * 32 * sizeof(uint2);
+  const int KS0 = KS / 2;
+  // where (k = u, n = bcol + e) sits in the fragment-ordered exchange buffer (32-bit word index; u even lanes store)
+  const int kk = u & 15;
+  size_t xw[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int lane_dst = (2 * q + e) * 4 + ((kk & 7) >> 1);
+    xw[e] = (((size_t)(u >> 4) * 4 + warp) * 32 + lane_dst) * 2 + (kk >> 3);
+  }
+  __syncthreads();
+
+  for (int s = 0; s < T; ++s) {
+    const int t = dir == 0 ? s : T - 1 - s;
+    const uint2* hprev = hbuf + (size_t)(dir * 2 + (s & 1)) * (hbytes / sizeof(uint2));
+    uint32_t* hnext = reinterpret_cast<uint32_t*>(hbuf + (size_t)(dir * 2 + ((s + 1) & 1)) * (hbytes / sizeof(uint2)));
+    if (tid == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      const uint32_t b0 = (uint32_t)((size_t)KS0 * 4 * 32 * sizeof(uint2)), b1 = (uint32_t)hbytes - b0;
+      mbar_arrive_expect_tx(&bar[0], b0);
+      bulk_g2s(hs, hprev, b0, &bar[0]);
+      mbar_arrive_expect_tx(&bar[1], b1);
+      bulk_g2s(hs + (size_t)KS0 * 4 * 32, hprev + (size_t)KS0 * 4 * 32, b1, &bar[1]);
+    }
+    float gxv[4][2];
+#pragma unroll
+    for (int gate = 0; gate < 4; ++gate)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        gxv[gate][e] = (bcol + e < B) ? gx[(((size_t)dir * T + t) * B + bcol + e) * 4 * H + gate * H + u] : 0.f;
+    float acc[2][2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+    mbar_wait(&bar[0], (uint32_t)(s & 1));
+#pragma unroll 4
+    for (int ks = 0; ks < KS0; ++ks) {
+      const uint2 bf = hs[((size_t)ks * 4 + warp) * 32 + lane];
+      mma_bf16_16816(acc[0][ks & 1], ws[(size_t)ks * 32 + lane], bf);
+      mma_bf16_16816(acc[1][ks & 1], ws[((size_t)KS + ks) * 32 + lane], bf);
+    }
+    mbar_wait(&bar[1], (uint32_t)(s & 1));
+#pragma unroll 4
+    for (int ks = KS0; ks < KS; ++ks) {
+      const uint2 bf = hs[((size_t)ks * 4 + warp) * 32 + lane];
+      mma_bf16_16816(acc[0][ks & 1], ws[(size_t)ks * 32 + lane], bf);
+      mma_bf16_16816(acc[1][ks & 1], ws[((size_t)KS + ks) * 32 + lane], bf);
+    }
+    // C fragment: [0],[1] = (row g, cols 2q, 2q+1), [2],[3] = (row g + 8, cols 2q, 2q+1)
+    float hval[2], ig[2], fg[2], gg[2], og[2], cn[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float pi = acc[0][0][e] + acc[0][1][e] + gxv[0][e];
+      const float pf = acc[0][0][2 + e] + acc[0][1][2 + e] + gxv[1][e];
+      const float pg = acc[1][0][e] + acc[1][1][e] + gxv[2][e];
+      const float po = acc[1][0][2 + e] + acc[1][1][2 + e] + gxv[3][e];
+      const bool on = t < len_b[e];
+      ig[e] = sigmoidf_(pi); fg[e] = sigmoidf_(pf); gg[e] = tanhf(pg); og[e] = sigmoidf_(po);
+      cn[e] = on ? fg[e] * c_state[e] + ig[e] * gg[e] : 0.f;
+      hval[e] = on ? og[e] * tanhf(cn[e]) : 0.f;
+      c_state[e] = cn[e];
+      // exchange: units u (even g) and u + 1 (lane + 4) share a 32-bit word
+      const float partner = __shfl_down_sync(0xffffffffu, hval[e], 4);
+      if ((g & 1) == 0) hnext[xw[e]] = pack_bf16(hval[e], partner);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+    dir_barrier_arrive(counters + dir);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int b = bcol + e;
+      if (b < B) {
+        if (gates_save) {
+          float* gs = gates_save + (((size_t)dir * T + t) * B + b) * 4 * H;
+          gs[u] = ig[e]; gs[H + u] = fg[e]; gs[2 * H + u] = gg[e]; gs[3 * H + u] = og[e];
+          c_save[(((size_t)dir * T + t) * B + b) * H + u] = cn[e];
+        }
+        h_all[((size_t)t * B + b) * 2 * H + dir * H + u] = hval[e];
+      }
+    }
+    dir_barrier_wait(counters + dir, d.G, phase);
+  }
+}
+
+constexpr int kLstmMmaBwdThreads = 256;   // 8 warps split K = 4H; each warp: 2 batch m-tiles x 8 units
+
+// dgbuf (bf16, A-fragment order): [2 dir][2 ping-pong][KS = 4H/16][2 m-tiles][32 lanes] uint4
+__global__ void __launch_bounds__(kLstmMmaBwdThreads, 1)
+lstm_bwd_mma_kernel(const float* __restrict__ dh_all, const float* __restrict__ whh, const int* __restrict__ lens,
+                    const float* __restrict__ gates_save, const float* __restrict__ c_save, LstmDims d,
+                    float* __restrict__ dgates_all, uint4* __restrict__ dgbuf, unsigned* __restrict__ counters) {
+  extern __shared__ __align__(128) uint8_t smraw[];
+  const int T = d.T, B = d.B, H = d.H;
+  const int J = 4 * H, KS = J / 16, KSW = (KS + 7) / 8;   // H % 8 == 0 -> J % 16 == 0; warp w owns k-steps [w KSW, ..)
+  const int dir = blockIdx.x / d.G, cta = blockIdx.x % d.G;
+  const int u0 = cta * 8;
+  uint2* wt = reinterpret_cast<uint2*>(smraw);                                            // [KS][32]  B fragments
+  uint4* dgs = reinterpret_cast<uint4*>(smraw + (size_t)KS * 32 * sizeof(uint2));          // [KS][2][32] A fragments
+  float* red = reinterpret_cast<float*>(smraw + (size_t)KS * 32 * sizeof(uint2) + (size_t)KS * 2 * 32 * sizeof(uint4));
+  __shared__ __align__(8) uint64_t bar[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1);
+    mbar_fence_init();
+  }
+  const float* W = whh + (size_t)dir * 4 * H * H;
+  for (int i = tid; i < KS * 32; i += kLstmMmaBwdThreads) {
+    const int ln = i & 31, ks = i >> 5;
+    const int gg = ln >> 2, qq = ln & 3;
+    const float* c = W + (size_t)(ks * 16 + 2 * qq) * H + u0 + gg;     // B[k = j][n = unit gg]
+    wt[i] = make_uint2(pack_bf16(c[0], c[H]), pack_bf16(c[(size_t)8 * H], c[(size_t)9 * H]));
+  }
+  // element-wise owner: unit ul = tid & 7, batch b = tid >> 3
+  const int ul = tid & 7, b = tid >> 3;
+  const int u = u0 + ul;
+  const bool mine = b < B;
+  const int len_b = mine ? lens[b] : 0;
+  float dc_state = 0.f;
+  unsigned phase = 0;
+  const size_t dwords = (size_t)KS * 2 * 32;          // uint4 per exchange buffer
+  // where (m = b, k = gate * H + u) sits in the exchange buffer (32-bit word index, even ul lanes store)
+  size_t xw[4];
+  {
+    const int mt = b >> 4, r = b & 15;
+#pragma unroll
+    for (int gate = 0; gate < 4; ++gate) {
+      const int j = gate * H + u, kk = j & 15;
+      const int lane_dst = (r & 7) * 4 + ((kk & 7) >> 1);
+      const int reg = (r >> 3) + 2 * (kk >> 3);
+      xw[gate] = (((size_t)(j >> 4) * 2 + mt) * 32 + lane_dst) * 4 + reg;
+    }
+  }
+  __syncthreads();
+
+  for (int s = 0; s < T; ++s) {
+    const int sf = T - 1 - s;
+    const int t = dir == 0 ? sf : T - 1 - sf;
+    const int t_prev = dir == 0 ? t - 1 : t + 1;
+    const uint4* dgnext = dgbuf + (size_t)(dir * 2 + (s & 1)) * dwords;
+    uint32_t* dgcur = reinterpret_cast<uint32_t*>(dgbuf + (size_t)(dir * 2 + ((s + 1) & 1)) * dwords);
+    if (tid == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      for (int w = 0; w < 8; ++w) {
+        const int ka = min(w * KSW, KS), kb = min(ka + KSW, KS);
+        if (kb > ka) {
+          const uint32_t cb = (uint32_t)((size_t)(kb - ka) * 2 * 32 * sizeof(uint4));
+          mbar_arrive_expect_tx(&bar[w], cb);
+          bulk_g2s(dgs + (size_t)ka * 2 * 32, dgnext + (size_t)ka * 2 * 32, cb, &bar[w]);
+        } else {
+          mbar_arrive(&bar[w]);
+        }
+      }
+    }
+    const bool on = mine && t < len_b;
+    float dh = 0.f, ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cn = 0.f, cp = 0.f;
+    if (mine) dh = dh_all[((size_t)t * B + b) * 2 * H + dir * H + u];
+    if (on) {
+      const float* gs = gates_save + (((size_t)dir * T + t) * B + b) * 4 * H;
+      ig = gs[u]; fg = gs[H + u]; gg = gs[2 * H + u]; og = gs[3 * H + u];
+      cn = c_save[(((size_t)dir * T + t) * B + b) * H + u];
+      const bool has_prev = (t_prev >= 0 && t_prev < T) && (t_prev < len_b);
+      cp = has_prev ? c_save[(((size_t)dir * T + t_prev) * B + b) * H + u] : 0.f;
+    }
+    // partial dh_rec[m = batch][n = unit] over this warp's K range
+    float acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
+    mbar_wait(&bar[warp], (uint32_t)(s & 1));
+#pragma unroll 4
+    for (int ks = min(warp * KSW, KS), ke = min(ks + KSW, KS); ks < ke; ++ks) {
+      const uint2 bf = wt[(size_t)ks * 32 + lane];
+      mma_bf16_16816(acc[0], dgs[((size_t)ks * 2) * 32 + lane], bf);
+      mma_bf16_16816(acc[1], dgs[((size_t)ks * 2 + 1) * 32 + lane], bf);
+    }
+    // red[warp][batch][unit]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float* rr = red + ((size_t)warp * 32 + mt * 16 + g) * 8 + 2 * q;
+      *reinterpret_cast<float2*>(rr) = make_float2(acc[mt][0], acc[mt][1]);
+      *reinterpret_cast<float2*>(rr + 8 * 8) = make_float2(acc[mt][2], acc[mt][3]);
+    }
+    __syncthreads();
+    float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int w = 0; w < 8; ++w) dh += red[((size_t)w * 32 + b) * 8 + ul];
+    if (on) {
+      const float tc = tanhf(cn);
+      const float dc = dh * og * (1.f - tc * tc) + dc_state;
+      d4[3] = dh * tc * og * (1.f - og);
+      d4[0] = dc * gg * ig * (1.f - ig);
+      d4[1] = dc * cp * fg * (1.f - fg);
+      d4[2] = dc * ig * (1.f - gg * gg);
+      dc_state = dc * fg;
+    } else {
+      dc_state = 0.f;
+    }
+#pragma unroll
+    for (int gate = 0; gate < 4; ++gate) {
+      const float partner = __shfl_down_sync(0xffffffffu, d4[gate], 1);   // unit ul + 1 of the same batch row
+      if ((ul & 1) == 0) dgcur[xw[gate]] = pack_bf16(d4[gate], partner);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+    dir_barrier_arrive(counters + dir);
+    if (mine) {
+      float* go = dgates_all + (((size_t)dir * T + t) * B + b) * J;
+      go[u] = d4[0]; go[H + u] = d4[1]; go[2 * H + u] = d4[2]; go[3 * H + u] = d4[3];
+    }
+    dir_barrier_wait(counters + dir, d.G, phase);
+  }
+}
+
 static int lstm_plan(int H, LstmDims* d) {
   // U <= 8 units per CTA, at most 74 CTAs per direction (both directions co-resident on 148 SMs)
   int U = (H + 73) / 74;
@@ -354,10 +630,13 @@ extern "C" size_t radtts_lstm_workspace_bytes(int B, int H) {
   return ((size_t)4 * 32 * H + (size_t)16 * 32 * H) * sizeof(float) + 256;
 }
 
+static bool lstm_mma_ok(int H, int precision) { return precision == RADTTS_PREC_BF16 && H % 8 == 0 && H >= 32 && H / 8 <= 74; }
+
 extern "C" int radtts_lstm_forward(const float* gx, const float* whh, const int* lens, int T, int B, int H,
                                    float* h_all, float* gates_save, float* c_save, void* ws, size_t ws_bytes,
-                                   void* stream) {
+                                   int precision, void* stream) {
   if (!gx || !whh || !lens || !h_all || !ws || T <= 0 || B <= 0 || H <= 0) return RADTTS_ERR_INVALID_ARG;
+  if (precision != RADTTS_PREC_FP32 && precision != RADTTS_PREC_BF16) return RADTTS_ERR_INVALID_ARG;
   if (B > kLstmMaxB) return RADTTS_ERR_UNSUPPORTED;
   if (ws_bytes < radtts_lstm_workspace_bytes(B, H)) return RADTTS_ERR_WORKSPACE;
   LstmDims d{T, B, H, 0, 0};
@@ -367,6 +646,22 @@ extern "C" int radtts_lstm_forward(const float* gx, const float* whh, const int*
   unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * 32 * H * sizeof(float));
   RB_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)4 * 32 * H * sizeof(float), st));
   RB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
+  if (lstm_mma_ok(H, precision)) {
+    d.U = 8;
+    d.G = H / 8;
+    const int KS = (H + 15) / 16;
+    const size_t smem = (size_t)2 * KS * 32 * sizeof(uint4) + (size_t)KS * 4 * 32 * sizeof(uint2);
+    static size_t configured_mma = 0;
+    if (smem > configured_mma) {
+      RB_CUDA(cudaFuncSetAttribute(lstm_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_mma = smem;
+    }
+    uint2* hb = reinterpret_cast<uint2*>(hbuf);
+    void* args[] = {(void*)&gx, (void*)&whh, (void*)&lens, (void*)&d, (void*)&h_all, (void*)&gates_save,
+                    (void*)&c_save, (void*)&hb, (void*)&counters};
+    RB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_fwd_mma_kernel, dim3(2 * d.G), dim3(kLstmMmaFwdThreads), args, smem, st));
+    return after_launch();
+  }
   const int R = 4 * d.U;
   const size_t smem = ((size_t)H * R + (size_t)H * kLstmLd + (size_t)16 * R * kLstmMaxB) * sizeof(float);
   if (smem > (size_t)kSmemBudget) return RADTTS_ERR_UNSUPPORTED;
@@ -383,9 +678,10 @@ extern "C" int radtts_lstm_forward(const float* gx, const float* whh, const int*
 
 extern "C" int radtts_lstm_backward(const float* dh_all, const float* whh, const int* lens, const float* gates_save,
                                     const float* c_save, int T, int B, int H, float* dgates_all, void* ws,
-                                    size_t ws_bytes, void* stream) {
+                                    size_t ws_bytes, int precision, void* stream) {
   if (!dh_all || !whh || !lens || !gates_save || !c_save || !dgates_all || !ws || T <= 0 || B <= 0 || H <= 0)
     return RADTTS_ERR_INVALID_ARG;
+  if (precision != RADTTS_PREC_FP32 && precision != RADTTS_PREC_BF16) return RADTTS_ERR_INVALID_ARG;
   if (B > kLstmMaxB) return RADTTS_ERR_UNSUPPORTED;
   if (ws_bytes < radtts_lstm_workspace_bytes(B, H)) return RADTTS_ERR_WORKSPACE;
   LstmDims d{T, B, H, 0, 0};
@@ -395,6 +691,23 @@ extern "C" int radtts_lstm_backward(const float* dh_all, const float* whh, const
   unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * 32 * H * sizeof(float));
   RB_CUDA(cudaMemsetAsync(dgbuf, 0, (size_t)16 * 32 * H * sizeof(float), st));
   RB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
+  if (lstm_mma_ok(H, precision)) {
+    d.U = 8;
+    d.G = H / 8;
+    const int KS = 4 * H / 16;
+    const size_t smem = (size_t)KS * 32 * sizeof(uint2) + (size_t)KS * 2 * 32 * sizeof(uint4) + (size_t)8 * 32 * 8 * sizeof(float);
+    if (smem > (size_t)kSmemBudget) return RADTTS_ERR_UNSUPPORTED;
+    static size_t configured_mma = 0;
+    if (smem > configured_mma) {
+      RB_CUDA(cudaFuncSetAttribute(lstm_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_mma = smem;
+    }
+    uint4* db = reinterpret_cast<uint4*>(dgbuf);
+    void* args[] = {(void*)&dh_all, (void*)&whh, (void*)&lens, (void*)&gates_save, (void*)&c_save, (void*)&d,
+                    (void*)&dgates_all, (void*)&db, (void*)&counters};
+    RB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_bwd_mma_kernel, dim3(2 * d.G), dim3(kLstmMmaBwdThreads), args, smem, st));
+    return after_launch();
+  }
   if (H % 2) return RADTTS_ERR_UNSUPPORTED;
   const size_t smem = ((size_t)4 * H * 8 + (size_t)2 * (H / 2) * kLstmLd + (size_t)32 * 8 * kLstmMaxB) * sizeof(float);
   if (smem > (size_t)kSmemBudget) return RADTTS_ERR_UNSUPPORTED;

@@ -46,12 +46,15 @@ class _BiLSTMFn(torch.autograd.Function):
         L = _lib.lib()
         nws = int(L.radtts_lstm_workspace_bytes(B, H))
         ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        # under autocast (where cuDNN would run the LSTM in half precision) the recurrent product uses bf16 operands
+        # on tensor cores; state, gates and outputs stay fp32.  The backward pass follows the forward's precision.
+        low_prec = torch.is_autocast_enabled()
         _lib.check(L.radtts_lstm_forward(_lib.ptr(gx), _lib.ptr(whh), _lib.ptr(lens), T, B, H, _lib.ptr(h_all),
                                          _lib.ptr(gates), _lib.ptr(cs), _lib.ptr(ws), ctypes.c_size_t(nws),
-                                         _lib.stream_of(x_tm)), "radtts_lstm_forward")
+                                         1 if low_prec else 0, _lib.stream_of(x_tm)), "radtts_lstm_forward")
         if need_bwd:
             ctx.save_for_backward(x_tm, lens, w_ih, whh, gates, cs, h_all)
-            ctx.low_prec = torch.is_autocast_enabled()   # the weight / input gradient GEMMs follow the forward's precision
+            ctx.low_prec = low_prec
         return h_all
 
     @staticmethod
@@ -67,7 +70,7 @@ class _BiLSTMFn(torch.autograd.Function):
         ws = torch.empty(nws, dtype=torch.uint8, device=dev)
         _lib.check(L.radtts_lstm_backward(_lib.ptr(dh_all), _lib.ptr(whh), _lib.ptr(lens), _lib.ptr(gates), _lib.ptr(cs),
                                           T, B, H, _lib.ptr(dg), _lib.ptr(ws), ctypes.c_size_t(nws),
-                                          _lib.stream_of(x_tm)), "radtts_lstm_backward")
+                                          1 if ctx.low_prec else 0, _lib.stream_of(x_tm)), "radtts_lstm_backward")
         mm = torch.bfloat16 if ctx.low_prec else torch.float32   # plain library GEMMs; bf16 under autocast
         dg2 = dg.reshape(2, T * B, 4 * H)
         dgm = dg2.to(mm)

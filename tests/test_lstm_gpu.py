@@ -67,3 +67,33 @@ def test_bilstm_spectral_norm_eval_forward(cuda_lib):
         assert torch.allclose(y, y_ref, rtol=1e-4, atol=2e-5), float((y - y_ref).abs().max())
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
+
+
+@pytest.mark.parametrize("In,H,B,T", [(1040, 520, 32, 61), (512, 256, 19, 37), (64, 40, 5, 23)])
+def test_bilstm_bf16_tensor_core_path(cuda_lib, In, H, B, T):
+    """Under autocast the recurrent product runs on tensor cores with bf16 W_hh / exchanged state (fp32 accumulate,
+    fp32 cell state and outputs).  Bar: outputs within 2e-2 abs of the fp32 kernel (|h| < 1), gradients within 5 %
+    relative (norm) -- the same order as cuDNN's own bf16 LSTM vs fp32."""
+    torch.manual_seed(0)
+    lstm = nn.LSTM(In, H, 1, batch_first=True, bidirectional=True).cuda()
+    x = (torch.randn(B, T, In, device="cuda") * 0.5).requires_grad_(True)
+    lens = torch.randint(max(1, T // 3), T + 1, (B,), device="cuda")
+    lens[0] = T
+    w = torch.randn(B, T, 2 * H, device="cuda")
+    y32 = lstm_ops.bilstm(lstm, x, lens)
+    (y32 * w).sum().backward()
+    ref = {n: p.grad.clone() for n, p in lstm.named_parameters()}
+    gx32 = x.grad.clone()
+    lstm.zero_grad()
+    x.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y16 = lstm_ops.bilstm(lstm, x, lens)
+    assert y16.dtype == torch.float32
+    (y16 * w).sum().backward()
+    assert float((y16 - y32).abs().max()) < 2e-2, float((y16 - y32).abs().max())
+    mask = (torch.arange(T, device="cuda")[None, :] >= lens[:, None])
+    assert float(y16[mask].abs().max()) == 0.0          # packed-sequence semantics: zeros beyond each length
+    assert float((x.grad - gx32).norm() / gx32.norm()) < 5e-2
+    for n, p in lstm.named_parameters():
+        err = float((p.grad - ref[n]).norm() / (ref[n].norm() + 1e-12))
+        assert err < 5e-2, (n, err)
