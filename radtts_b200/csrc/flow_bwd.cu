@@ -185,9 +185,15 @@ static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const P
   // bf16: every problem of this flow goes into ONE batched tcgen05 launch; fp32: SIMT launches with atomics.
   WgradBatch batch;
   batch.rows_alloc = rows;
+  ColsumBatch<T> sums;
+  // the tcgen05 wgrad stores every element of its output (no split-K, no atomics): only the SIMT path needs zeros
+  constexpr bool kNeedZero = sizeof(T) != 2;
   auto wgrad = [&](const WgradProb& p, bool accumulate) -> int {
     if constexpr (sizeof(T) == 2) {
       if (batch.add(p, accumulate)) return 0;
+      // batch full: SIMT fallback accumulates with atomics, so a non-accumulating problem needs its window zeroed
+      if (!accumulate)
+        RB_CUDA(cudaMemset2DAsync(p.out, (size_t)p.so_n * sizeof(float), 0, (size_t)p.C * sizeof(float), p.N, st));
     }
     return launch_wgrad_simt<T, T>(p, pv.hdr(), rows, st);
   };
@@ -205,38 +211,39 @@ static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const P
     WgradProb p{gparams, L.end_kpad, 0, d.z_ld, r, nl * nc, l * nc, nc, 0, tmp, ldt, 1};
     RB_TRY(wgrad(p, true));
   }
-  RB_TRY((launch_colsum<T>(gparams, L.end_kpad, 0, d.z_ld, meta, 0, 0, k, pv.hdr(), rows, tmp + nc, ldt, false, st)));
+  RB_TRY(sums.add(gparams, L.end_kpad, 0, d.z_ld, 0, 0, tmp + nc, ldt, false, st));
   for (int i = 0; i < nl; ++i) {
     const T* gui = gu + (size_t)i * rows * nc;
     const T* gvi = gv + (size_t)i * rows * nc;
     // res_skip_i: dW[n][c] = sum_r g_u_i[r][n] x_{i+1}[r][c]
-    RB_CUDA(cudaMemsetAsync(g.g_w_rs[i], 0, (size_t)nc * nc * sizeof(float), st));
+    if (kNeedZero) RB_CUDA(cudaMemsetAsync(g.g_w_rs[i], 0, (size_t)nc * nc * sizeof(float), st));
     {
       WgradProb p{gui, nc, 0, nc, x + (size_t)(i + 1) * rows * nc, nc, 0, nc, 0, g.g_w_rs[i], nc, 1};
       RB_TRY(wgrad(p, false));
     }
-    RB_TRY((launch_colsum<T>(gui, nc, 0, nc, meta, 0, 0, k, pv.hdr(), rows, g.g_b_rs[i], 1, true, st)));
+    RB_TRY(sums.add(gui, nc, 0, nc, 0, 0, g.g_b_rs[i], 1, true, st));
     // in_layer_i (tap-major output [t][n][c]): dW[t][n][c] = sum_r g_v_i[r][n] x_i[r + (t - half) d][c]
-    RB_CUDA(cudaMemsetAsync(g.g_w_in[i], 0, (size_t)nc * nc * k * sizeof(float), st));
+    if (kNeedZero) RB_CUDA(cudaMemsetAsync(g.g_w_in[i], 0, (size_t)nc * nc * k * sizeof(float), st));
     for (int t = 0; t < k; ++t) {
       WgradProb p{gvi, nc, 0, nc, x + (size_t)i * rows * nc, nc, 0, nc, (t - k / 2) << i,
                   g.g_w_in[i] + (size_t)t * nc * nc, nc, 1};
       RB_TRY(wgrad(p, false));
     }
     // bias sits outside the partial-conv renormalisation: g_bias = sum_r g_v / ratio
-    RB_TRY((launch_colsum<T>(gvi, nc, 0, nc, meta, d.partial_padding, i, k, pv.hdr(), rows, g.g_b_in[i], 1, true, st)));
+    RB_TRY(sums.add(gvi, nc, 0, nc, d.partial_padding, i, g.g_b_in[i], 1, true, st));
   }
   // start: the two K segments land directly in the reference layout [z0 (h) | ctx (n_ctx)]
   {
     const int ldo = h + d.n_ctx;
-    RB_CUDA(cudaMemsetAsync(g.g_w_start, 0, (size_t)nc * ldo * sizeof(float), st));
+    if (kNeedZero) RB_CUDA(cudaMemsetAsync(g.g_w_start, 0, (size_t)nc * ldo * sizeof(float), st));
     WgradProb pc{gx0, nc, 0, nc, f.ctx, L.ctx_ld, 0, d.n_ctx, 0, g.g_w_start + h, ldo, 1};
     RB_TRY(wgrad(pc, false));
     WgradProb pz{gx0, nc, 0, nc, f.z0, 128, 0, h, 0, g.g_w_start, ldo, 1};
     RB_TRY(wgrad(pz, false));
-    RB_TRY((launch_colsum<T>(gx0, nc, 0, nc, meta, 0, 0, k, pv.hdr(), rows, g.g_b_start, 1, true, st)));
+    RB_TRY(sums.add(gx0, nc, 0, nc, 0, 0, g.g_b_start, 1, true, st));
   }
   RB_TRY(batch.launch(pv.hdr(), st));
+  RB_TRY(sums.launch(meta, k, pv.hdr(), rows, st));
   end_grad_unpack_kernel<<<grid_for((size_t)2 * h * ldt), 256, 0, st>>>(tmp, ldt, h, nc, g.g_w_end, g.g_b_end);
   RB_TRY(after_launch());
   return 0;

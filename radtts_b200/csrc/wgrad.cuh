@@ -139,22 +139,37 @@ __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, flo
   v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
 }
 
+constexpr int kColsumMaxItems = 2 * RADTTS_MAX_LAYERS + 2;
+struct ColsumItem {
+  const void* G;
+  float* out;
+  int ldg, gcol, N, partial, log2d, ostride;
+};
+struct ColsumParams {
+  ColsumItem it[kColsumMaxItems];
+  RowMeta meta;
+  const int* plan;
+  int rows_alloc, chunk, ksize;
+};
+// All bias-gradient column sums of a flow in one launch: blockIdx.z = problem.
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ G, int ldg, int gcol, int N, RowMeta meta,
-                                                     int partial, int log2d, int ksize, const int* __restrict__ plan,
-                                                     int rows_alloc, int chunk, float* __restrict__ out, int ostride) {
-  const int rows_used = plan ? plan[0] : rows_alloc;
+__global__ void __launch_bounds__(256) colsum_kernel(const ColsumParams p) {
+  const ColsumItem& it = p.it[blockIdx.z];
+  const int N = it.N, ldg = it.ldg;
+  if ((int)blockIdx.x * 128 >= N) return;
+  const T* G = reinterpret_cast<const T*>(it.G);
+  const int rows_used = p.plan ? p.plan[0] : p.rows_alloc;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n0 = blockIdx.x * 128 + tx * 4;
-  const int r_begin = blockIdx.y * chunk, r_end = min(r_begin + chunk, rows_used);
+  const int r_begin = blockIdx.y * p.chunk, r_end = min(r_begin + p.chunk, rows_used);
   float s[4] = {0.f, 0.f, 0.f, 0.f};
   if (n0 < N) {   // N is a multiple of 4 for every caller (channel counts are multiples of 16)
 #pragma unroll 4
     for (int r = r_begin + ty; r < r_end; r += 8) {
       float v[4];
-      load4<T>(G + (size_t)r * ldg + gcol + n0, v);
+      load4<T>(G + (size_t)r * ldg + it.gcol + n0, v);
       float sc = 1.f;
-      if (partial) sc = meta.valid(r) ? 1.f / meta.ratio(r, log2d, ksize) : 0.f;
+      if (it.partial) sc = p.meta.valid(r) ? 1.f / p.meta.ratio(r, it.log2d, p.ksize) : 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) s[i] = fmaf(v[i], sc, s[i]);
     }
@@ -169,21 +184,32 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ G, in
       float t = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-      atomicAdd(out + (size_t)n * ostride, t);
+      atomicAdd(it.out + (size_t)n * it.ostride, t);
     }
   }
 }
 
+// Collects the column-sum problems of a flow; launch() runs them all at once.
 template <typename T>
-inline int launch_colsum(const T* G, int ldg, int gcol, int N, RowMeta meta, int partial, int log2d, int ksize,
-                         const int* plan, int rows_alloc, float* out, int ostride, bool zero_first, cudaStream_t st) {
-  if (zero_first) RB_CUDA(cudaMemsetAsync(out, 0, (size_t)N * ostride * sizeof(float), st));
-  if ((N % 4) || (ldg % 4) || (gcol % 4)) return RADTTS_ERR_INVALID_ARG;
-  const int chunk = 256;
-  dim3 grid(ceil_div(N, 128), ceil_div(rows_alloc, chunk));
-  colsum_kernel<T><<<grid, 256, 0, st>>>(G, ldg, gcol, N, meta, partial, log2d, ksize, plan, rows_alloc, chunk, out, ostride);
-  return after_launch();
-}
+struct ColsumBatch {
+  ColsumParams p{};
+  int n = 0, max_n = 0;
+  int add(const T* G, int ldg, int gcol, int N, int partial, int log2d, float* out, int ostride, bool zero_first,
+          cudaStream_t st) {
+    if (n == kColsumMaxItems || (N % 4) || (ldg % 4) || (gcol % 4)) return RADTTS_ERR_INVALID_ARG;
+    if (zero_first) RB_CUDA(cudaMemsetAsync(out, 0, (size_t)N * ostride * sizeof(float), st));
+    p.it[n++] = ColsumItem{G, out, ldg, gcol, N, partial, log2d, ostride};
+    if (N > max_n) max_n = N;
+    return 0;
+  }
+  int launch(RowMeta meta, int ksize, const int* plan, int rows_alloc, cudaStream_t st) {
+    if (n == 0) return 0;
+    p.meta = meta; p.plan = plan; p.rows_alloc = rows_alloc; p.chunk = 256; p.ksize = ksize;
+    dim3 grid(ceil_div(max_n, 128), ceil_div(rows_alloc, p.chunk), n);
+    colsum_kernel<T><<<grid, 256, 0, st>>>(p);
+    return after_launch();
+  }
+};
 
 }  // namespace rb
 
