@@ -75,13 +75,44 @@ class AttentionCTCLoss(nn.Module):
     def __init__(self, blank_logprob=-1):
         super().__init__()
         self.blank_logprob = blank_logprob
+        self._prefetched = None     # (attn_logprob tensor, loss, side stream)
+        self._side = None
 
     def forward(self, attn_logprob, in_lens, out_lens):
         B, _, T1, T2 = attn_logprob.shape
+        pre, self._prefetched = self._prefetched, None
+        if pre is not None and pre[0] is attn_logprob:
+            torch.cuda.current_stream(attn_logprob.device).wait_stream(pre[2])
+            return pre[1]
         if attn_logprob.is_cuda and 2 * T2 + 1 <= 1024:
             from . import ops
             return ops.attention_ctc_loss(attn_logprob, in_lens, out_lens, self.blank_logprob)
         return self.forward_torch(attn_logprob, in_lens, out_lens)
+
+    def prefetch_from(self, attention_module):
+        """Overlap: the fused CTC kernel occupies one SM per utterance for ~1 ms (a serial alpha/beta recursion over the
+        frames) and needs nothing but attn_logprob.  This hooks the model's ConvAttention so that the kernel is
+        launched on a side stream the moment the attention is computed, and runs underneath MAS / the context LSTM /
+        the decoder flows; forward() later just joins the stream.  Returns the hook handle."""
+        def hook(module, args, kwargs, output):
+            attn_logprob = output[1]
+            if not (torch.is_grad_enabled() and attn_logprob.is_cuda and 2 * attn_logprob.shape[3] + 1 <= 1024):
+                return None
+            out_lens = args[2]
+            in_lens = kwargs.get("key_lens", args[4] if len(args) > 4 else None)
+            if in_lens is None or out_lens is None:
+                return None
+            from . import ops
+            dev = attn_logprob.device
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            cur = torch.cuda.current_stream(dev)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                loss = ops.attention_ctc_loss(attn_logprob, in_lens, out_lens, self.blank_logprob)
+            self._prefetched = (attn_logprob, loss, self._side)
+            return None
+        return attention_module.register_forward_hook(hook, with_kwargs=True)
 
     def forward_torch(self, attn_logprob, in_lens, out_lens):
         """Batched PyTorch formulation (CPU tensors, or text longer than the fused kernel supports)."""

@@ -25,6 +25,10 @@ class TrainStep:
                     dist.broadcast(t.data, 0)
         self.criterion = rloss.RADTTSLoss(sigma=1.0, n_group_size=model.n_group_size, loss_weights=loss_weights)
         self.bin_loss = rloss.AttentionBinarizationLoss()
+        if next(model.parameters()).is_cuda and hasattr(model, "attention"):
+            # launch the attention CTC kernel as soon as ConvAttention is done, on a side stream (captured as a parallel
+            # branch of the step's CUDA graph): it then overlaps the rest of the forward pass
+            self._ctc_hook = self.criterion.attn_ctc_loss.prefetch_from(model.attention)
         self.loss_weights = loss_weights
         self.bf16 = bf16
         self.binarize = binarize_attention
