@@ -138,6 +138,11 @@ def time_region(fn, steps, world):
     return max_over_ranks(e0.elapsed_time(e1), world)
 
 
+# DRAM traffic of one in_layer launch on this workload from the committed ncu capture (33.45 MB read + 0.24 MB written;
+# algorithmic = 22.3 MB activations in + 10.5 MB weights + 22.3 MB out, the output is still in L2 when the launch ends)
+IN_LAYER_DRAM_BYTES_NCU = 33.69e6
+
+
 def in_layer_kernel_probe(model, batch, iters=10):
     """Times the dominant kernel (bf16 tcgen05 row-GEMM of one dilated in_layer conv, K = 5 x 1024) in isolation
     with CUDA events on the launching stream; returns (ms per launch, frame groups per launch)."""
@@ -338,7 +343,10 @@ def main():
         achieved = groups * IN_LAYER_FLOP_PER_GROUP / (k_ms / 1e3) / 1e12
         roofline = {"bound": "tensor", "kernel": "rowgemm_tc_kernel<EpiBiasAct<bf16>> (WN in_layer, dilated k5 1024->1024)",
                     "achieved": round(achieved, 1), "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                    "frac": round(achieved / peaks["tf_burst"], 4), "traffic": None, "peak_source": peaks["source"] + " burst",
+                    "frac": round(achieved / peaks["tf_burst"], 4), "traffic": IN_LAYER_DRAM_BYTES_NCU,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
+                                      "profiles/r01b_rowgemm_tc_ncu_raw.csv (same workload)",
+                    "peak_source": peaks["source"] + " burst",
                     "ms_per_launch": round(k_ms, 4),
                     "step_frac_of_sustained_peak": round(value / world * FLOP_PER_FRAME_TRAIN / 1e12 / peaks["tf_sustained"], 4)}
     extra = None
