@@ -18,6 +18,8 @@ _forced_precision = None
 
 
 _direct_grad = False
+flow_backward_done = None   # optional callable(): invoked right after the flow stack's backward has enqueued its last
+                            # kernel (with direct accumulation on, every WN gradient is final in .grad at that point)
 
 
 def set_direct_grad_accumulation(on):

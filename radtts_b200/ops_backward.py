@@ -103,10 +103,21 @@ def flow_stack_backward(saved, g_zout, g_log_s):
         if not direct:
             for j in idx_v + idx_g:
                 out[j] = outs[j]
+        else:
+            # the small WN gradients (biases, `end`) take the same route, so that every gradient of the parameter
+            # network is final in .grad when this function returns (the data-parallel trainer starts their all-reduce
+            # right here, underneath the rest of the backward pass); only the 1x1 conv's LUS factors go through autograd
+            for j in range(1, n_per):
+                t, sk = out[j], sinks[j]
+                if t is not None and sk is not None and sk.grad is not None and sk.grad.dtype == t.dtype:
+                    sk.grad.add_(t.reshape(sk.grad.shape))
+                    out[j] = None
         for j, t in enumerate(out):
             if t is not None:
                 assert t.numel() == int(torch.Size(w_shapes[base + j]).numel()), (j, t.shape, w_shapes[base + j])
                 grads[base + j] = t.reshape(w_shapes[base + j])
         g_z = g_zin
+    if ops.flow_backward_done is not None:
+        ops.flow_backward_done()
     g_ctx_out = g_ctx if ctx_dtype == torch.float32 else g_ctx.to(ctx_dtype)
     return (g_z, g_ctx_out, None, None, None, None, None, None) + tuple(grads)

@@ -1,6 +1,8 @@
 """One optimisation step of RADTTS on the B200 hot path, mirroring the reference training loop body
 (reference train.py:385-422): forward under autocast -> RADTTSLoss (+ binarization loss) -> backward ->
 gradient all-reduce (DDP/NCCL) -> clip -> optimizer step."""
+import os
+
 import torch
 
 from . import loss as rloss
@@ -35,6 +37,20 @@ class TrainStep:
         self.use_bin_loss = use_binarization_loss
         self.grad_clip_val = grad_clip_val
         params = [p for p in model.parameters() if p.requires_grad]
+        self.n_bulk = 0
+        if ddp and fused_optimizer and hasattr(model, "flows"):
+            # flat-buffer order: the decoder flows' parameter networks first (94 % of the bytes; their gradients are
+            # final when the flow stack's backward returns), everything else after -- two contiguous all-reduce regions
+            bulk_ids, bulk = set(), []
+            for f in model.flows:
+                tfn = getattr(f, "affine_tfn", None)
+                net = getattr(tfn, "affine_param_predictor", None)
+                for p in ([] if net is None else net.parameters()):
+                    if p.requires_grad and id(p) not in bulk_ids:
+                        bulk_ids.add(id(p))
+                        bulk.append(p)
+            params = bulk + [p for p in params if id(p) not in bulk_ids]
+            self.n_bulk = sum((p.numel() + 3) // 4 * 4 for p in bulk)
         self.capturable = bool(capturable)
         self.fused_optimizer = bool(fused_optimizer)
         if self.fused_optimizer:
@@ -44,6 +60,13 @@ class TrainStep:
             # gradients live in the optimizer's flat buffer and this class reduces them itself (no DDP hooks): let
             # the flow stack's backward add weight_v / weight_g gradients straight into it
             ops.set_direct_grad_accumulation(True)
+            if self.world > 1 and self.n_bulk > 0 and not os.environ.get("RADTTS_NO_COMM_OVERLAP"):
+                dev = next(model.parameters()).device
+                self.comm = torch.cuda.Stream(device=dev)
+                # external: inside the captured step this becomes an event-record NODE that the eagerly launched NCCL
+                # all-reduce (comm stream) can wait on -- the collective then overlaps the rest of the backward graph
+                self.ev_bulk = torch.cuda.Event(external=True)
+                ops.flow_backward_done = lambda: self.ev_bulk.record(torch.cuda.current_stream(dev))
         else:
             self.optimizer = torch.optim.RAdam(params, lr=lr, weight_decay=weight_decay, foreach=True,
                                                capturable=self.capturable)
@@ -116,10 +139,24 @@ class TrainStep:
 
     def _allreduce(self):
         # data-parallel gradient exchange on the flat buffer: the reference does one flat all-reduce after backward
-        # (distributed.py:133-140); 128 MB chunks let NCCL pipeline over NVLink / NVSwitch
+        # (distributed.py:133-140); 128 MB chunks let NCCL pipeline over NVLink / NVSwitch.  The flow stack's region
+        # (first n_bulk elements) is reduced on the comm stream as soon as ev_bulk fires, i.e. while the LSTM /
+        # attention / encoder part of the backward pass is still running; the remainder follows at the end.
         import torch.distributed as dist
-        for chunk in self.optimizer.grad.split(32 << 20):
-            dist.all_reduce(chunk)
+        g = self.optimizer.grad
+        n_bulk = self.n_bulk if getattr(self, "comm", None) is not None else 0
+        if n_bulk > 0:
+            cur = torch.cuda.current_stream(g.device)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(self.ev_bulk)
+                for chunk in g[:n_bulk].split(32 << 20):
+                    dist.all_reduce(chunk)
+            for chunk in g[n_bulk:].split(32 << 20):
+                dist.all_reduce(chunk)
+            cur.wait_stream(self.comm)
+        else:
+            for chunk in g.split(32 << 20):
+                dist.all_reduce(chunk)
 
     def _update(self):
         if self.grad_clip_val > 0:
