@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "flow_common.cuh"
 #include "flow_layout.cuh"
+#include "invconv.cuh"
 #include "frameplan.cuh"
 #include "rowgemm.cuh"
 #include "rowgemm_tc.cuh"
@@ -445,14 +446,23 @@ static int flowstep_impl(const radtts_flow_dims& d, const uint8_t* base, const P
   g.w = base + L.w_inv; g.ldw = d.z_ld; g.N = d.z_ld;
   if (!inverse) {
     g.seg[0] = Seg{buf.zin, d.z_ld, 0, 0, d.z_ld};
-    EpiInvConv<T> e{buf.zmid, buf.zout, reinterpret_cast<T*>(buf.z0), d.c_off, h, d.z_ld, meta};
-    RB_TRY(launch_rowgemm_simt(g, e, st));
+    if (d.z_ld % 4 == 0 && d.z_ld <= kInvMaxLd) {
+      RB_TRY(launch_invconv_rows<T>(buf.zin, reinterpret_cast<const float*>(base + L.w_inv), d.z_ld, pv.hdr(),
+                                    pv.rows_alloc, meta, 1, buf.zmid, buf.zout, d.c_off + h, reinterpret_cast<T*>(buf.z0),
+                                    d.c_off, h, st));
+    } else {
+      EpiInvConv<T> e{buf.zmid, buf.zout, reinterpret_cast<T*>(buf.z0), d.c_off, h, d.z_ld, meta};
+      RB_TRY(launch_rowgemm_simt(g, e, st));
+    }
     return wn_and_coupling<T>(d, base, L, pv, buf, 0, st);
   }
   extract_z0_kernel<T><<<grid_for((size_t)pv.rows_alloc * d.z_ld), 256, 0, st>>>(
       buf.zin, d.z_ld, d.c_off, h, pv.hdr(), buf.zmid, reinterpret_cast<T*>(buf.z0));
   RB_TRY(after_launch());
   RB_TRY(wn_and_coupling<T>(d, base, L, pv, buf, 1, st));
+  if (d.z_ld % 4 == 0 && d.z_ld <= kInvMaxLd)
+    return launch_invconv_rows<float>(buf.zmid, reinterpret_cast<const float*>(base + L.w_inv), d.z_ld, pv.hdr(),
+                                      pv.rows_alloc, meta, 1, buf.zout, nullptr, 0, nullptr, 0, 0, st);
   g.seg[0] = Seg{buf.zmid, d.z_ld, 0, 0, d.z_ld};
   EpiStoreF32 e{buf.zout, d.z_ld, meta, 1};
   return launch_rowgemm_simt(g, e, st);

@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 
 #include "flow_common.cuh"
+#include "invconv.cuh"
 #include "wgrad.cuh"
 
 namespace rb {
@@ -176,7 +177,10 @@ static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const P
   gd.nseg = 1;
   gd.seg[0] = Seg{g.g_zmid, d.z_ld, 0, 0, d.z_ld};
   gd.w = base + L.w_inv_t; gd.ldw = d.z_ld; gd.N = d.z_ld;
-  {
+  if (d.z_ld % 4 == 0 && d.z_ld <= kInvMaxLd) {
+    RB_TRY(launch_invconv_rows<float>(g.g_zmid, reinterpret_cast<const float*>(base + L.w_inv_t), d.z_ld, pv.hdr(), rows,
+                                      meta, 1, g.g_zin, nullptr, 0, nullptr, 0, 0, st));
+  } else {
     EpiStoreF32 e{g.g_zin, d.z_ld, meta, 1};
     RB_TRY(launch_rowgemm_simt(gd, e, st));
   }
@@ -200,8 +204,12 @@ static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const P
   // 1x1 conv: dW_full[c][j] = sum_r g_zmid[r][c] zin[r][j]   (fp32 always)
   {
     RB_CUDA(cudaMemsetAsync(g.g_w_inv_full, 0, (size_t)d.z_ld * d.z_ld * sizeof(float), st));
-    WgradProb p{g.g_zmid, d.z_ld, 0, d.z_ld, f.zin, d.z_ld, 0, d.z_ld, 0, g.g_w_inv_full, d.z_ld, 1};
-    RB_TRY((launch_wgrad_simt<float, float>(p, pv.hdr(), rows, st)));
+    if (d.z_ld == kInvMaxLd) {
+      RB_TRY(launch_invconv_wgrad(g.g_zmid, f.zin, pv.hdr(), rows, g.g_w_inv_full, st));
+    } else {
+      WgradProb p{g.g_zmid, d.z_ld, 0, d.z_ld, f.zin, d.z_ld, 0, d.z_ld, 0, g.g_w_inv_full, d.z_ld, 1};
+      RB_TRY((launch_wgrad_simt<float, float>(p, pv.hdr(), rows, st)));
+    }
   }
   // end: interleaved rows into scratch, the n_layers K-blocks of r accumulate; bias = column sums of g_params
   float* tmp = g.scratch_f32;
