@@ -5,6 +5,7 @@ frame-plan bookkeeping.  All math of the hot path happens inside libradtts_b200.
 missing or an input is not on a CUDA device these functions raise (no CPU fallback).
 """
 import ctypes
+import os
 
 import torch
 
@@ -696,12 +697,13 @@ class _ConvAttnFn(torch.autograd.Function):
 
 def conv_attention(att, queries, keys, mask, key_lens, attn_prior):
     """ConvAttention.forward (reference common.py:886-924).  The key/query projections are five small convs
-    (< 0.5 % of the step's FLOPs) run through cuDNN; everything after them -- the part that dominates memory
+    (< 0.5 % of the step's FLOPs) run through cuDNN (bf16 under autocast); everything after them -- the part that dominates memory
     traffic in the reference -- is the fused CUDA kernel 3."""
     _lib.require_cuda(queries, keys)
-    with torch.autocast(device_type="cuda", enabled=False):
-        k_enc = att.key_proj(keys.float())
-        q_enc = att.query_proj(queries.float())
+    # the projections follow the ambient autocast state exactly as in the reference (common.py:900-901: only the
+    # softmax / log part is forced to fp32); the fused kernel takes their outputs in fp32
+    k_enc = att.key_proj(keys).float()
+    q_enc = att.query_proj(queries).float()
     if key_lens is None and mask is not None:
         key_lens = (~mask.squeeze(-1)).sum(1)
     if mask is None:

@@ -38,5 +38,13 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     ts.step(b)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+print("==== kernels only")
+from torch.autograd import DeviceType
+ks = [e for e in prof.key_averages() if e.device_type == DeviceType.CUDA]
+ks.sort(key=lambda e: -e.device_time_total)
+tot = sum(e.device_time_total for e in ks)
+print("total kernel time %.2f ms, %d launches" % (tot / 1e3, sum(e.count for e in ks)))
+for e in ks[:90]:
+    print("%9.1f us %5d x %8.2f  %s" % (e.device_time_total, e.count, e.device_time_total / e.count, e.key[:120]))
 print("==== CPU")
 print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=40, max_name_column_width=60))
