@@ -263,6 +263,17 @@ RADTTS_API int radtts_affine_apply(const float* z, const float* params, int B, i
 RADTTS_API int radtts_pointwise_conv_small(const float* x, const float* w, int B, int C, int T, float* y, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Hard-attention context: context = bmm(text_enc, attn_hard^T) of reference radtts.py:399 as a gather by
+ * the frame -> token index radtts_mas_forward produces, and its backward (segment sum per token).
+ *   text_enc (B, C, T2), frame_to_token (B, T1) int32 (-1 beyond out_len), context (B, C, T1); float32.
+ *   Frame 0 also receives token 0 when the path does not start there (the reference's opt[0,0] = 1, alignment.py:59).
+ * ---------------------------------------------------------------------------------------------- */
+RADTTS_API int radtts_context_gather(const float* text_enc, const int32_t* frame_to_token, int B, int C, int T1, int T2,
+                                     float* context, void* stream);
+RADTTS_API int radtts_context_scatter(const float* grad_context, const int32_t* frame_to_token, int B, int C, int T1,
+                                      int T2, float* grad_text_enc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Persistent bidirectional LSTM recurrence (context BiLSTM, reference radtts.py:284-293, and the text
  * encoder BiLSTM, common.py:359-371 -- a packed-sequence cuDNN call in the reference).  One cooperative kernel per
  * pass runs the whole time loop; the x-projection GEMM and the weight-gradient GEMMs stay outside (plain GEMMs).

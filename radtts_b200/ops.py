@@ -740,3 +740,37 @@ def attention_ctc_loss(attn_logprob, in_lens, out_lens, blank_logprob=-1.0):
     """AttentionCTCLoss.forward (reference loss.py:118-135) as one fused CUDA launch, no host synchronisation."""
     _lib.require_cuda(attn_logprob)
     return _AttnCTCFn.apply(attn_logprob, in_lens, out_lens, float(blank_logprob))
+
+
+class _ContextGatherFn(torch.autograd.Function):
+    """context = bmm(text_enc, attn_hard^T) for a binarized alignment (reference radtts.py:399), as a gather by the
+    frame -> token index of the MAS kernel; backward = per-token segment sum.  No gradient reaches the alignment."""
+
+    @staticmethod
+    def forward(ctx, text_enc, f2t):
+        text = text_enc.float().contiguous()
+        B, C, T2 = text.shape
+        T1 = f2t.shape[1]
+        out = torch.empty((B, C, T1), dtype=torch.float32, device=text.device)
+        _lib.check(_lib.lib().radtts_context_gather(_lib.ptr(text), _lib.ptr(f2t), B, C, T1, T2, _lib.ptr(out),
+                                                    _lib.stream_of(text)), "radtts_context_gather")
+        ctx.save_for_backward(f2t)
+        ctx.shape = (B, C, T1, T2)
+        ctx.in_dtype = text_enc.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (f2t,) = ctx.saved_tensors
+        B, C, T1, T2 = ctx.shape
+        g = g.float().contiguous()
+        out = torch.empty((B, C, T2), dtype=torch.float32, device=g.device)
+        _lib.check(_lib.lib().radtts_context_scatter(_lib.ptr(g), _lib.ptr(f2t), B, C, T1, T2, _lib.ptr(out),
+                                                     _lib.stream_of(g)), "radtts_context_scatter")
+        return out.to(ctx.in_dtype), None
+
+
+def hard_attention_context(text_enc, frame_to_token):
+    """text_enc (B, C, T2), frame_to_token (B, T1) int32 from alignment.mas_forward(..., return_indices=True)."""
+    _lib.require_cuda(text_enc, frame_to_token)
+    return _ContextGatherFn.apply(text_enc, frame_to_token.contiguous())

@@ -226,14 +226,25 @@ class RADTTS(nn.Module):
                 keys = torch.cat((keys, spk.detach()), 1)
             attn_soft, attn_logprob = self.attention(mel, keys, out_lens, attn_mask, key_lens=in_lens,
                                                      attn_prior=attn_prior)
-            if binarize_attention:
-                attn = self.binarize_attention(attn_soft, in_lens, out_lens)
+            if binarize_attention and type(self).binarize_attention is RADTTS.binarize_attention \
+                    and attn_soft.is_cuda and attn_soft.shape[2] * 4 <= 48 * 1024:
+                # the MAS kernel also returns each frame's token: the context "bmm with a one-hot matrix" of the
+                # reference (radtts.py:399) becomes a gather (forward) / per-token segment sum (backward)
+                with torch.no_grad():
+                    attn, f2t, _ = alignment.mas_forward(attn_soft, in_lens, out_lens, is_prob=True, return_indices=True)
                 attn_hard = attn
                 if self.attn_straight_through_estimator:
                     attn_hard = attn_soft + (attn_hard - attn_soft).detach()
+                context = ops.hard_attention_context(text_enc, f2t)
             else:
-                attn = attn_soft
-            context = torch.bmm(text_enc, attn.squeeze(1).transpose(1, 2))
+                if binarize_attention:
+                    attn = self.binarize_attention(attn_soft, in_lens, out_lens)
+                    attn_hard = attn
+                    if self.attn_straight_through_estimator:
+                        attn_hard = attn_soft + (attn_hard - attn_soft).detach()
+                else:
+                    attn = attn_soft
+                context = torch.bmm(text_enc, attn.squeeze(1).transpose(1, 2))
 
         f0_bias = 0
         if self.use_unvoiced_bias:
