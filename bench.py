@@ -235,6 +235,7 @@ def cpu_baseline(B, T1, T2, steps=1, warmup=0):
     batch = synth.synth_batch(B, T1, T2, seed=99)
     fps, sec_per_step, frames = ots.time_steps(sd, batch, steps=steps, warmup=warmup, backward=True, threads=threads)
     return {"value": round(fps, 2), "unit": "mel frames/s", "cores": threads, "kind": "port",
+            "ms_per_step_sample": round(sec_per_step * 1e3, 1),
             "sample": "oracle hot path (ConvAttention + serial MAS + 8 decoder flows fwd+bwd, fp32) on B=%d x %d frames x "
                       "%d tokens, %d step(s), %.1f s/step" % (B, T1, T2, steps, sec_per_step)}
 
@@ -243,11 +244,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(2, args.t1, args.t2, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    # each "step" of this arm = the oracle's train step on a bounded sample (4 of the 32 utterances of a full batch):
+    # ~2 s of CPU work per step on 16 cores, so a --steps 8 --warmup 3 run still ends within a minute
+    cb = cpu_baseline(4, args.t1, args.t2, steps=max(1, args.steps), warmup=max(0, min(1, args.warmup)))
     line = {"impl": "reference", "metric": "mel frames/s, RADTTS decoder train step (fwd+bwd+MAS)", "value": cb["value"],
             "unit": "mel frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
-            "data": "synthetic", "config": workload_config(args), "cpu_baseline": cb,
+            "ms_per_step": cb["ms_per_step_sample"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic", "config": workload_config(args), "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": "mel frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -360,7 +363,7 @@ def main():
         dist.barrier()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cb = cpu_baseline(1, args.t1, args.t2, steps=1, warmup=0)
+            cb = cpu_baseline(4, args.t1, args.t2, steps=3, warmup=1)
         except Exception as e:  # the baseline is reported, never required
             cb = {"value": None, "error": repr(e)}
     if rank == 0:
