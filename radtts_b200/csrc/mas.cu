@@ -25,7 +25,8 @@ namespace rb {
 constexpr int kMasMaxDpWarps = 18;   // T2 <= 576
 constexpr int kMasFillWarps = 4;
 constexpr int kMasMaxStages = 32;
-constexpr int kMasEdge = 128;        // rows of slack in the inter-warp edge ring
+constexpr int kMasEdge = 256;        // slots of each inter-warp edge ring (1 KB, 1 KB aligned)
+constexpr uint32_t kMasSentinel = 0x7fa00001u;   // a SIGNALLING NaN: no fp32 add can ever produce it (see dp_warp)
 
 struct MasPlan {
   int W;                // DP warps
@@ -47,13 +48,16 @@ static int make_plan(int B, int T1, int T2, MasPlan* p) {
   uint32_t off = 2 * kMasMaxStages * 8 + 256;            // mbarriers + progress counters
   p->path_off = off;            off += (uint32_t)round_up(T1 * 2, 16);
   p->dur_off = off;             off += (uint32_t)round_up(T2 * 4, 16);
-  p->edge_off = off;            off += (uint32_t)(W * kMasEdge * 4);
+  p->edge_off = off;            off += (uint32_t)((W + 2) * kMasEdge * 4);   // ring W = dump ring of the lanes != 31; + 1 KB so
+                                                                             // that the kernel can align the rings to 1 KB
   off = (uint32_t)round_up((int)off, 128);
   p->bits_off = off;
   const uint32_t bits_bytes = (uint32_t)round_up(T1 * W * 4, 128);
-  const uint32_t need_stages = (uint32_t)(W + 3);         // the wavefront skew is one chunk per DP warp
+  const uint32_t need_stages = 5;                         // DP warps trail each other by a row or two: a few stages of
+                                                          // prefetch depth are enough, the rest goes into longer chunks
   auto stage_bytes_for = [&](int rows) { return (uint32_t)round_up(rows * T2 * 4 + 256, 128); };  // + alignment slack
-  if (off + bits_bytes + need_stages * stage_bytes_for(4) <= (uint32_t)kSmemBudget) {
+  const uint32_t budget = (uint32_t)kSmemBudget - 4096u;  // head-room for the prefetch-overshoot row
+  if (off + bits_bytes + need_stages * stage_bytes_for(4) <= budget) {
     p->bits_in_smem = 1;
     p->ring_off = off + bits_bytes;
     p->bits_ws_bytes = 0;
@@ -62,16 +66,20 @@ static int make_plan(int B, int T1, int T2, MasPlan* p) {
     p->ring_off = off;
     p->bits_ws_bytes = (size_t)B * T1 * W * 4;
   }
-  // rows per chunk (= per-chunk synchronisation amortised over that many rows): as many as W+3 stages allow, <= 16
+  // rows per chunk (= per-chunk synchronisation amortised over that many rows): as many as 5 stages allow, <= 16
   for (r = 16; r > 1; --r)
-    if (p->ring_off + need_stages * stage_bytes_for(r) <= (uint32_t)kSmemBudget) break;
+    if (p->ring_off + need_stages * stage_bytes_for(r) <= budget) break;
   p->rows_per_chunk = r;
   p->stage_bytes = stage_bytes_for(r);
-  int st = (int)((kSmemBudget - p->ring_off) / p->stage_bytes);
+  const uint32_t row_pad = (uint32_t)round_up(T2 * 4, 16);   // one row of prefetch overshoot behind the last stage
+  int st = (int)((kSmemBudget - p->ring_off - row_pad) / p->stage_bytes);
   if (st > kMasMaxStages) st = kMasMaxStages;
+  // a DP warp may lead its right neighbour by at most `stages` chunks (ring back-pressure); the edge ring between
+  // them is never checked for overrun, so that lead must stay below its kMasEdge slots
+  if (W > 1 && (st + 1) * r > kMasEdge - 8) st = (kMasEdge - 8) / r - 1;
   if (st < 2) return RADTTS_ERR_UNSUPPORTED;
   p->stages = st;
-  p->smem_bytes = p->ring_off + (uint32_t)st * p->stage_bytes;
+  p->smem_bytes = p->ring_off + (uint32_t)st * p->stage_bytes + row_pad;
   return 0;
 }
 
@@ -113,6 +121,15 @@ __device__ __forceinline__ void st_shared_pred(uint32_t addr, uint32_t v, int pr
   asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.shared.b32 [%0], %1; }" ::"r"(addr), "r"(v), "r"(pred)
                : "memory");
 }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_pred(uint64_t* bar, bool pred) {
+  asm volatile("{ .reg .pred q; .reg .b64 t; setp.ne.s32 q, %1, 0; @q mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(
+                   smem_u32(bar)),
+               "r"((int)pred)
+               : "memory");
+}
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
@@ -145,86 +162,101 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 
 // One DP warp: columns [32 warp, 32 warp + 32) of the utterance, one per lane, R rows per ring stage.
-// Everything the row loop touches is addressed with 32-bit shared-window addresses computed once per chunk (a generic
-// pointer re-derives the window base with S2UR inside the loop), the stage index / phase are running counters (a
-// runtime `c % stages` costs ~130 cycles per chunk), and single-lane stores are PREDICATED, never branched: two
-// divergent single-lane branches in the row body cost ~120 cycles per row on sm_100 (tools/mas_micro.cu).
+//
+// Hand-off between neighbouring warps is PER ROW and the value is its own flag: lane 31 of warp w stores its running score
+// of row r into slot r of ring w; lane 0 of warp w+1 needs exactly that number for row r+1, spins while the slot holds
+// the sentinel and writes the sentinel back once it has the value.  The sentinel is a signalling NaN: every score is
+// the result of an fp32 add, which can only produce quiet NaNs, so no computed value collides with it (row 0 takes
+// `a + 0.0f` for that reason).  A 32-bit shared-memory store is atomic: no fence, no separate progress counter, and
+// warp w+1 trails warp w by ~1 row instead of one ring stage.  Ring overrun is impossible by construction: a warp can
+// lead its neighbour by at most stages * R rows (the cost ring's back-pressure), which make_plan keeps below the ring.
+//
+// Instruction diet (W >= 10 warps share 4 issue ports): all addresses are running 32-bit shared-window pointers, the
+// decision word is stored by all lanes to the same address, the edge value by all lanes to a lane-dependent address
+// (lane 31 -> the real ring, the others -> a dump ring), i.e. no predicates and no divergent single-lane branches
+// (two of those cost ~120 cycles per row, tools/mas_micro.cu).
 template <bool kBitsInSmem, bool kFirstWarp>
-__device__ __forceinline__ void dp_warp(uint64_t* full, uint64_t* empty, int* done, float* edge, uint8_t* ring,
-                                        uint32_t* bits_s, uint32_t* bits_g, const MasPlan& plan, size_t slab, int T2,
-                                        int olen, int nchunks, int Wl, int warp, int lane, bool probe_cta) {
+__device__ __forceinline__ void dp_warp(uint64_t* full, uint64_t* empty, float* edge, uint8_t* ring, uint32_t* bits_s,
+                                        uint32_t* bits_g, const MasPlan& plan, size_t slab, int T2, int olen, int nchunks,
+                                        int warp, int lane, bool probe) {
   const int W = plan.W, R = plan.rows_per_chunk, stages = plan.stages;
   const int col = warp * 32 + lane;
   const int ccol = min(col, T2 - 1);
   const float nanv = __int_as_float(0x7fc00000);
-  const int is_l0 = (lane == 0), is_l31 = (lane == 31);
+  const bool is_l0 = lane == 0;
   const uint32_t row_bytes = (uint32_t)T2 * 4u;
-  const uint32_t my_edge = smem_u32(edge + (size_t)warp * kMasEdge);
-  const uint32_t up_edge = smem_u32(edge + (size_t)(kFirstWarp ? 0 : warp - 1) * kMasEdge);
-  const uint32_t bits_base = smem_u32(bits_s + warp);
+  constexpr uint32_t kRingBytes = kMasEdge * 4u;
+  auto ring_next = [](uint32_t p) { return (p & ~(kRingBytes - 1u)) | ((p + 4u) & (kRingBytes - 1u)); };
+  // pm: where this lane publishes its score (slot of the current row); pe: slot of the previous row in the upstream ring
+  uint32_t pm = smem_u32(edge + (size_t)(lane == 31 ? warp : W) * kMasEdge);
+  uint32_t pe = smem_u32(edge + (size_t)(kFirstWarp ? W : warp - 1) * kMasEdge);
+  uint32_t pb = smem_u32(bits_s + warp);                       // decision word of (row, warp), smem variant
+  uint32_t* pbg = bits_g + warp;                                // ... global variant
   const uint32_t ring_base = smem_u32(ring) + (uint32_t)ccol * 4u;
   uint32_t mis = (uint32_t)((slab * 4) & 127);          // offset of the chunk's first byte inside its stage
   const uint32_t mis_step = ((uint32_t)R * row_bytes) & 127u;
   float v = -CUDART_INF_F;
-  int up_seen = 0;                       // rows warp-1 is known to have finished
-  int down_seen = 0;                     // rows warp+1 is known to have finished (back-pressure on the edge ring)
+  float e = __uint_as_float(kMasSentinel);               // upstream score of the previous row (sentinel = not read yet)
   int s = 0;
   uint32_t phase = 0;
-  long long tw_wait = 0, tw_rows = 0, tw_post = 0, tqs = clock64();
-  const bool probe = probe_cta && warp == Wl - 1 && lane == 0;
+  long long tw_wait = 0, tw_rows = 0, tqs = clock64();
   for (int c = 0, r0 = 0; c < nchunks; ++c, r0 += R) {
     const int r1 = min(r0 + R, olen);
-    if constexpr (kFirstWarp) {
-      mbar_wait(&full[s], phase);
-    } else {
-      // row i needs row i-1 of warp-1 (its last lane): wait until warp-1 has finished this chunk.  Having seen that,
-      // the chunk's bytes are in the ring too (warp-1 waited on full[s], directly or transitively), so only warp 0
-      // polls the mbarrier.
-      while (up_seen < r1) up_seen = ld_acquire_s32(&done[warp - 1]);
-    }
-    if (warp + 1 < Wl) {
-      while (r1 - down_seen > kMasEdge - 1) down_seen = ld_acquire_s32(&done[warp + 1]);
-    }
+    mbar_wait(&full[s], phase);
     const long long tq1 = clock64();
-    const uint32_t st = ring_base + (uint32_t)s * plan.stage_bytes + mis;
-    float a = lds_f32(st);
+    uint32_t pa = ring_base + (uint32_t)s * plan.stage_bytes + mis;
+    float a = lds_f32(pa);
+    pa += row_bytes;
     int row = r0;
-    if (row == 0) {                      // alignment.py:41-42: row 0 may only sit on token 0
-      v = (col == 0) ? a : -CUDART_INF_F;
-      st_shared_pred(my_edge, __float_as_uint(v), is_l31);
-      a = lds_f32(st + (uint32_t)min(1, r1 - 1) * row_bytes);
+    if (row == 0) {                      // alignment.py:41-42: row 0 may only sit on token 0 (and carries no decisions)
+      v = (col == 0) ? __fadd_rn(a, 0.f) : -CUDART_INF_F;
+      sts_u32(pm, __float_as_uint(v));
+      pm = ring_next(pm);
+      a = lds_f32(pa);
+      pa += row_bytes;
+      pb += (uint32_t)W * 4u;
+      pbg += W;
+      if (!kFirstWarp) e = lds_f32(pe);
       row = 1;
     }
     for (; row < r1; ++row) {
-      const float an = lds_f32(st + (uint32_t)(min(row + 1, r1 - 1) - r0) * row_bytes);   // clamped, never branched
+      const float an = lds_f32(pa);      // next row's cost: unconditional (the ring is padded by one row)
+      pa += row_bytes;
       float left = __shfl_up_sync(0xffffffffu, v, 1);
       if constexpr (kFirstWarp) {
-        if (lane == 0) left = nanv;      // NaN >= x is false: column 0 never takes the diagonal
+        left = is_l0 ? nanv : left;      // NaN >= x is false: column 0 never takes the diagonal
       } else {
-        left = lds_f32_pred(up_edge + (uint32_t)((row - 1) & (kMasEdge - 1)) * 4u, is_l0, left);
+        {
+          unsigned spins = 0;              // bounded like every other wait: a protocol bug must trap, not hang
+          while (__any_sync(0xffffffffu, __float_as_uint(e) == kMasSentinel)) {
+            e = lds_f32(pe);
+            if (++spins > (1u << 24)) __trap();
+          }
+        }
+        sts_u32(pe, kMasSentinel);       // consumed: hand the slot back
+        pe = ring_next(pe);
+        left = is_l0 ? e : left;
+        e = lds_f32(pe);                 // prefetch the next row's value (re-polled above if not there yet)
       }
       const bool diag = (left >= v);
       v = __fadd_rn(a, diag ? left : v);
       const uint32_t w = __ballot_sync(0xffffffffu, diag);
-      if constexpr (kBitsInSmem) st_shared_pred(bits_base + (uint32_t)(row * W) * 4u, w, is_l0);
-      else st_global_pred(&bits_g[(size_t)row * W + warp], w, is_l0);
-      st_shared_pred(my_edge + (uint32_t)(row & (kMasEdge - 1)) * 4u, __float_as_uint(v), is_l31);
+      if constexpr (kBitsInSmem) { sts_u32(pb, w); pb += (uint32_t)W * 4u; }
+      else { *pbg = w; pbg += W; }
+      sts_u32(pm, __float_as_uint(v));
+      pm = ring_next(pm);
       a = an;
     }
     const long long tq2 = clock64();
     __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(&empty[s]);
-      st_release_s32(&done[warp], r1);
-    }
+    mbar_arrive_pred(&empty[s], is_l0);
     if (++s == stages) { s = 0; phase ^= 1u; }
     mis = (mis + mis_step) & 127u;
-    const long long tq3 = clock64();
-    if (probe) { tw_wait += tq1 - tqs; tw_rows += tq2 - tq1; tw_post += tq3 - tq2; }
-    tqs = tq3;
+    if (probe) { tw_wait += tq1 - tqs; tw_rows += tq2 - tq1; }
+    tqs = clock64();
   }
-  if (probe) {
-    g_mas_timeline[8] = tw_wait; g_mas_timeline[9] = tw_rows; g_mas_timeline[10] = tw_post;
+  if (probe && lane == 0) {
+    g_mas_timeline[8] = tw_wait; g_mas_timeline[9] = tw_rows; g_mas_timeline[10] = 0;
     g_mas_timeline[11] = nchunks; g_mas_timeline[12] = R;
   }
 }
@@ -240,10 +272,10 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMasMaxStages;
-  int* done = reinterpret_cast<int*>(smem + 2 * kMasMaxStages * 8);   // done[w] = rows finished by DP warp w
   uint16_t* path = reinterpret_cast<uint16_t*>(smem + plan.path_off);
   int* dur_s = reinterpret_cast<int*>(smem + plan.dur_off);
-  float* edge = reinterpret_cast<float*>(smem + plan.edge_off);      // [W][kMasEdge]
+  // [W + 1][kMasEdge] rings on a 1 KB boundary of the shared WINDOW (the wrap-around of a slot pointer is a bit mask)
+  float* edge = reinterpret_cast<float*>(smem + plan.edge_off + ((1024u - ((smem_u32(smem) + plan.edge_off) & 1023u)) & 1023u));
   uint8_t* ring = smem + plan.ring_off;
 
   const int b = blockIdx.x;
@@ -276,7 +308,7 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
     mbar_fence_init();
   }
   for (int j = tid; j < T2; j += nthreads) dur_s[j] = 0;
-  if (tid < 64) done[tid] = 0;
+  for (int i = tid; i < (W + 1) * kMasEdge; i += nthreads) reinterpret_cast<uint32_t*>(edge)[i] = kMasSentinel;
   if (active)
     for (int j = tid; j < W; j += nthreads) put_bits(j, 0u);   // row 0 carries no decisions
   __syncthreads();
@@ -315,11 +347,11 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
     // ------------------------------ DP warps (skewed wavefront) ------------------------------
     if (warp < Wl) {
       if (warp == 0)
-        dp_warp<kBitsInSmem, true>(full, empty, done, edge, ring, bits_s, bits_g, plan, slab, T2, olen, nchunks, Wl,
-                                   warp, lane, b == 0);
+        dp_warp<kBitsInSmem, true>(full, empty, edge, ring, bits_s, bits_g, plan, slab, T2, olen, nchunks, warp, lane,
+                                   b == 0 && warp == Wl - 1);
       else
-        dp_warp<kBitsInSmem, false>(full, empty, done, edge, ring, bits_s, bits_g, plan, slab, T2, olen, nchunks, Wl,
-                                    warp, lane, b == 0);
+        dp_warp<kBitsInSmem, false>(full, empty, edge, ring, bits_s, bits_g, plan, slab, T2, olen, nchunks, warp, lane,
+                                    b == 0 && warp == Wl - 1);
       if (b == 0 && tid == 0) { g_mas_timeline[1] = gtime(); g_mas_timeline[7] = (unsigned long long)clock64(); }
     }
   } else {
@@ -343,12 +375,16 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
         const unsigned long long x = ((unsigned long long)hi << 32) | lo;
         win = (uint32_t)(x >> ((j & 31) + 1));
       }
+      // all 32 windows into registers FIRST: with the shuffle issued inside the step loop it sat on the dependent
+      // chain (shfl 24 + 3 ALU ops = ~40 cycles per row); hoisted, a step is shift / and / sub = ~15 cycles
+      uint32_t wk[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) wk[k] = __shfl_sync(0xffffffffu, win, k);
       int pos = 31, mycol = 0;
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
-        const uint32_t wk = __shfl_sync(0xffffffffu, win, k);
-        if (lane == k) mycol = j - (31 - pos);
-        pos -= (int)((wk >> pos) & 1u);                // rows <= 0 have win == 0: no movement
+        mycol = (lane == k) ? j - (31 - pos) : mycol;
+        pos -= (int)((wk[k] >> pos) & 1u);             // rows <= 0 have win == 0: no movement
       }
       if (row >= 0) path[row] = (uint16_t)mycol;
       j -= (31 - pos);
