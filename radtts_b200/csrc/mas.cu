@@ -17,12 +17,14 @@
 // to column 0, and the unconditional opt[0,0] = 1 (alignment.py:59).
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace rb {
 
-constexpr int kMasMaxDpWarps = 18;   // T2 <= 576
+constexpr int kMasMaxDpWarps = 9;    // T2 <= 576
 constexpr int kMasFillWarps = 4;
 constexpr int kMasMaxStages = 32;
 constexpr int kMasEdge = 256;        // slots of each inter-warp edge ring (1 KB, 1 KB aligned)
@@ -30,6 +32,8 @@ constexpr uint32_t kMasSentinel = 0x7fa00001u;   // a SIGNALLING NaN: no fp32 ad
 
 struct MasPlan {
   int W;                // DP warps
+  int NC;               // column sets per lane (1..4)
+  int Wb;               // decision words per row (NC per DP warp)
   int threads;
   int rows_per_chunk;   // rows per bulk copy (= progress-publication granularity)
   int stages;
@@ -40,9 +44,17 @@ struct MasPlan {
 };
 
 static int make_plan(int B, int T1, int T2, MasPlan* p) {
-  const int W = (T2 + 31) / 32;
+  // NC column sets per lane (lane l of warp w owns columns 32 NC w + l + 32 k, k < NC) so that at most ~4 DP warps run,
+  // one per scheduler: more warps cost ~8 cycles per row each (issue interference), more columns per lane are almost free
+  // (independent dependency chains that interleave)
+  // measured (64 x 2000 x T2, cycles per row of the last warp): NC=1: 161 (T2=300, 10 warps); NC=2: 159 (5 warps);
+  // NC=3: 190 (4 warps) -- two sets per lane it is, three or four only where the warp limit requires them
+  const int NC = T2 <= 32 ? 1 : (T2 <= 64 * kMasMaxDpWarps ? 2 : 4);
+  const int W = (T2 + 32 * NC - 1) / (32 * NC);
   if (W > kMasMaxDpWarps || T1 > 65535) return RADTTS_ERR_UNSUPPORTED;
   p->W = W;
+  p->NC = NC;
+  p->Wb = NC * W;                    // 32-bit decision words per lattice row
   p->threads = (W + 1 + kMasFillWarps) * 32;
   int r = 1;
   uint32_t off = 2 * kMasMaxStages * 8 + 256;            // mbarriers + progress counters
@@ -52,7 +64,7 @@ static int make_plan(int B, int T1, int T2, MasPlan* p) {
                                                                              // that the kernel can align the rings to 1 KB
   off = (uint32_t)round_up((int)off, 128);
   p->bits_off = off;
-  const uint32_t bits_bytes = (uint32_t)round_up(T1 * W * 4, 128);
+  const uint32_t bits_bytes = (uint32_t)round_up(T1 * p->Wb * 4, 128);
   const uint32_t need_stages = 5;                         // DP warps trail each other by a row or two: a few stages of
                                                           // prefetch depth are enough, the rest goes into longer chunks
   auto stage_bytes_for = [&](int rows) { return (uint32_t)round_up(rows * T2 * 4 + 256, 128); };  // + alignment slack
@@ -64,7 +76,7 @@ static int make_plan(int B, int T1, int T2, MasPlan* p) {
   } else {
     p->bits_in_smem = 0;
     p->ring_off = off;
-    p->bits_ws_bytes = (size_t)B * T1 * W * 4;
+    p->bits_ws_bytes = (size_t)B * T1 * p->Wb * 4;
   }
   // rows per chunk (= per-chunk synchronisation amortised over that many rows): as many as 5 stages allow, <= 16
   for (r = 16; r > 1; --r)
@@ -124,6 +136,14 @@ __device__ __forceinline__ void st_shared_pred(uint32_t addr, uint32_t v, int pr
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void sts_u32x2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts_u32x2_pred(uint32_t addr, uint32_t a, uint32_t b, int pred) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %3, 0; @q st.shared.v2.b32 [%0], {%1, %2}; }" ::"r"(addr), "r"(a), "r"(b),
+               "r"(pred)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_pred(uint64_t* bar, bool pred) {
   asm volatile("{ .reg .pred q; .reg .b64 t; setp.ne.s32 q, %1, 0; @q mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(
                    smem_u32(bar)),
@@ -175,87 +195,156 @@ __device__ __forceinline__ unsigned long long gtime() {
 // decision word is stored by all lanes to the same address, the edge value by all lanes to a lane-dependent address
 // (lane 31 -> the real ring, the others -> a dump ring), i.e. no predicates and no divergent single-lane branches
 // (two of those cost ~120 cycles per row, tools/mas_micro.cu).
-template <bool kBitsInSmem, bool kFirstWarp>
+template <bool kBitsInSmem, bool kFirstWarp, int NC>
 __device__ __forceinline__ void dp_warp(uint64_t* full, uint64_t* empty, float* edge, uint8_t* ring, uint32_t* bits_s,
                                         uint32_t* bits_g, const MasPlan& plan, size_t slab, int T2, int olen, int nchunks,
                                         int warp, int lane, bool probe) {
-  const int W = plan.W, R = plan.rows_per_chunk, stages = plan.stages;
-  const int col = warp * 32 + lane;
-  const int ccol = min(col, T2 - 1);
+  const int W = plan.W, Wb = plan.Wb, R = plan.rows_per_chunk, stages = plan.stages;
+  // NC column sets per lane: lane l owns columns c_k = 32 NC warp + 32 k + l, so that each warp ballot is already a word
+  // of 32 consecutive columns.  Left neighbour of c_k: lane l-1's c_k, and for lane 0 lane 31's c_{k-1} (k > 0) or the
+  // upstream warp's last column (k = 0): ONE rotate-by-one shuffle per column set delivers both cases.
+  const int col0 = warp * 32 * NC + lane;
   const float nanv = __int_as_float(0x7fc00000);
   const bool is_l0 = lane == 0;
+  const int rot = (lane + 31) & 31;
   const uint32_t row_bytes = (uint32_t)T2 * 4u;
-  constexpr uint32_t kRingBytes = kMasEdge * 4u;
-  auto ring_next = [](uint32_t p) { return (p & ~(kRingBytes - 1u)) | ((p + 4u) & (kRingBytes - 1u)); };
-  // pm: where this lane publishes its score (slot of the current row); pe: slot of the previous row in the upstream ring
-  uint32_t pm = smem_u32(edge + (size_t)(lane == 31 ? warp : W) * kMasEdge);
-  uint32_t pe = smem_u32(edge + (size_t)(kFirstWarp ? W : warp - 1) * kMasEdge);
-  uint32_t pb = smem_u32(bits_s + warp);                       // decision word of (row, warp), smem variant
-  uint32_t* pbg = bits_g + warp;                                // ... global variant
-  const uint32_t ring_base = smem_u32(ring) + (uint32_t)ccol * 4u;
+  // Single-lane stores are PREDICATED: a divergent branch per store costs ~60 cycles (tools/mas_micro.cu).
+  const uint32_t my_ring = smem_u32(edge + (size_t)warp * kMasEdge);   // written by lane 31 only
+  const int l0i = lane == 0, l31i = lane == 31;
+  const uint32_t up_base = smem_u32(edge + (size_t)(kFirstWarp ? W : warp - 1) * kMasEdge);
+  uint32_t pb = smem_u32(bits_s + NC * warp);                  // decision words of (row, warp), smem variant
+  uint32_t* pbg = bits_g + NC * warp;                          // ... global variant
+  const uint32_t ring_base = smem_u32(ring);
+  uint32_t cofs[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) cofs[k] = (uint32_t)min(col0 + 32 * k, T2 - 1) * 4u;
   uint32_t mis = (uint32_t)((slab * 4) & 127);          // offset of the chunk's first byte inside its stage
   const uint32_t mis_step = ((uint32_t)R * row_bytes) & 127u;
-  float v = -CUDART_INF_F;
-  float e = __uint_as_float(kMasSentinel);               // upstream score of the previous row (sentinel = not read yet)
+  float v[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) v[k] = -CUDART_INF_F;
   int s = 0;
   uint32_t phase = 0;
   long long tw_wait = 0, tw_rows = 0, tqs = clock64();
+  long long n_spin = 0;
+  const bool probe0 = kFirstWarp && blockIdx.x == 0;
+  auto slot = [&](int q) { return up_base + ((uint32_t)q & (kMasEdge - 1)) * 4u; };
+  // one lattice row: compare / select / add exactly as the reference, one ballot per column set, decision words stored
+  // by lane 0, the last column's score published by lane 31
+  auto step = [&](const float (&a)[NC], float e_up, int row, uint32_t pbits, uint32_t* pbitsg) {
+    float t[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) t[k] = __shfl_sync(0xffffffffu, v[k], rot);
+    uint32_t w[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const float left = is_l0 ? (k == 0 ? e_up : t[k - 1]) : t[k];   // first warp: e_up = NaN, NaN >= x is false
+      const bool d = (left >= v[k]);
+      v[k] = __fadd_rn(a[k], d ? left : v[k]);
+      w[k] = __ballot_sync(0xffffffffu, d);
+    }
+    if constexpr (kBitsInSmem) {
+      if constexpr (NC == 1) st_shared_pred(pbits, w[0], l0i);
+      else if constexpr (NC == 2) sts_u32x2_pred(pbits, w[0], w[1], l0i);
+      else {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) st_shared_pred(pbits + 4u * k, w[k], l0i);
+      }
+    } else if (is_l0) {
+#pragma unroll
+      for (int k = 0; k < NC; ++k) pbitsg[k] = w[k];
+    }
+    st_shared_pred(my_ring + ((uint32_t)row & (kMasEdge - 1)) * 4u, __float_as_uint(v[NC - 1]), l31i);
+  };
+  float eu[4] = {nanv, nanv, nanv, nanv};   // upstream scores for the current group of 4 rows (first warp: NaN)
   for (int c = 0, r0 = 0; c < nchunks; ++c, r0 += R) {
     const int r1 = min(r0 + R, olen);
     mbar_wait(&full[s], phase);
     const long long tq1 = clock64();
-    uint32_t pa = ring_base + (uint32_t)s * plan.stage_bytes + mis;
-    float a = lds_f32(pa);
+    uint32_t pa = ring_base + (uint32_t)s * plan.stage_bytes + mis;   // row pointer (column offsets added per load)
+    float a[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) a[k] = lds_f32(pa + cofs[k]);
     pa += row_bytes;
     int row = r0;
     if (row == 0) {                      // alignment.py:41-42: row 0 may only sit on token 0 (and carries no decisions)
-      v = (col == 0) ? __fadd_rn(a, 0.f) : -CUDART_INF_F;
-      sts_u32(pm, __float_as_uint(v));
-      pm = ring_next(pm);
-      a = lds_f32(pa);
+      v[0] = (col0 == 0) ? __fadd_rn(a[0], 0.f) : -CUDART_INF_F;
+      st_shared_pred(my_ring, __float_as_uint(v[NC - 1]), l31i);
+#pragma unroll
+      for (int k = 0; k < NC; ++k) a[k] = lds_f32(pa + cofs[k]);
       pa += row_bytes;
-      pb += (uint32_t)W * 4u;
-      pbg += W;
-      if (!kFirstWarp) e = lds_f32(pe);
+      pb += (uint32_t)Wb * 4u;
+      pbg += Wb;
       row = 1;
     }
-    for (; row < r1; ++row) {
-      const float an = lds_f32(pa);      // next row's cost: unconditional (the ring is padded by one row)
-      pa += row_bytes;
-      float left = __shfl_up_sync(0xffffffffu, v, 1);
-      if constexpr (kFirstWarp) {
-        left = is_l0 ? nanv : left;      // NaN >= x is false: column 0 never takes the diagonal
-      } else {
-        {
-          unsigned spins = 0;              // bounded like every other wait: a protocol bug must trap, not hang
-          while (__any_sync(0xffffffffu, __float_as_uint(e) == kMasSentinel)) {
-            e = lds_f32(pe);
-            if (++spins > (1u << 24)) __trap();
-          }
+    // groups of 4 rows: ONE wait (on the newest upstream score the group needs; lane 31 of the upstream warp stores its
+    // scores in row order, so the older three are then in place too), 4 hand-backs, and a spin-free body the compiler
+    // can unroll and overlap.
+    while (row + 4 <= r1) {
+      if constexpr (!kFirstWarp) {
+        eu[3] = lds_f32(slot(row + 2));
+        unsigned spins = 0;              // bounded like every other wait: a protocol bug must trap, not hang
+        while (__any_sync(0xffffffffu, __float_as_uint(eu[3]) == kMasSentinel)) {
+          __nanosleep(32);               // a tight spin steals issue slots from the DP warps sharing this scheduler
+          eu[3] = lds_f32(slot(row + 2));
+          ++n_spin;
+          if (++spins > (1u << 22)) __trap();
         }
-        sts_u32(pe, kMasSentinel);       // consumed: hand the slot back
-        pe = ring_next(pe);
-        left = is_l0 ? e : left;
-        e = lds_f32(pe);                 // prefetch the next row's value (re-polled above if not there yet)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) eu[k] = lds_f32(slot(row - 1 + k));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st_shared_pred(slot(row - 1 + k), kMasSentinel, l0i);   // hand the slots back
       }
-      const bool diag = (left >= v);
-      v = __fadd_rn(a, diag ? left : v);
-      const uint32_t w = __ballot_sync(0xffffffffu, diag);
-      if constexpr (kBitsInSmem) { sts_u32(pb, w); pb += (uint32_t)W * 4u; }
-      else { *pbg = w; pbg += W; }
-      sts_u32(pm, __float_as_uint(v));
-      pm = ring_next(pm);
-      a = an;
+      float an[4][NC];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)        // costs of the next four rows (overshoots the chunk by one row at most)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) an[j][k] = lds_f32(pa + (uint32_t)j * row_bytes + cofs[k]);
+      pa += 4u * row_bytes;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        step(a, eu[j], row + j, pb + (uint32_t)(j * Wb) * 4u, pbg + (size_t)j * Wb);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) a[k] = an[j][k];
+      }
+      pb += 4u * (uint32_t)Wb * 4u;
+      pbg += 4 * Wb;
+      row += 4;
+    }
+    for (; row < r1; ++row) {            // chunk tail (< 4 rows)
+      float n[NC];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) n[k] = lds_f32(pa + cofs[k]);   // next row: unconditional (padded ring)
+      pa += row_bytes;
+      float e = nanv;
+      if constexpr (!kFirstWarp) {
+        const uint32_t s0 = slot(row - 1);
+        e = lds_f32(s0);
+        unsigned spins = 0;
+        while (__any_sync(0xffffffffu, __float_as_uint(e) == kMasSentinel)) {
+          __nanosleep(32);
+          e = lds_f32(s0);
+          if (++spins > (1u << 22)) __trap();
+        }
+        st_shared_pred(s0, kMasSentinel, l0i);   // consumed: hand the slot back
+      }
+      step(a, e, row, pb, pbg);
+      pb += (uint32_t)Wb * 4u;
+      pbg += Wb;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) a[k] = n[k];
     }
     const long long tq2 = clock64();
     __syncwarp();
     mbar_arrive_pred(&empty[s], is_l0);
     if (++s == stages) { s = 0; phase ^= 1u; }
     mis = (mis + mis_step) & 127u;
-    if (probe) { tw_wait += tq1 - tqs; tw_rows += tq2 - tq1; }
+    if (probe || probe0) { tw_wait += tq1 - tqs; tw_rows += tq2 - tq1; }
     tqs = clock64();
   }
+  if (probe0 && !probe && lane == 0) g_mas_timeline[13] = tw_rows;
   if (probe && lane == 0) {
+    g_mas_timeline[14] = n_spin;
     g_mas_timeline[8] = tw_wait; g_mas_timeline[9] = tw_rows; g_mas_timeline[10] = 0;
     g_mas_timeline[11] = nchunks; g_mas_timeline[12] = R;
   }
@@ -286,7 +375,7 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
   const int olen = (int)(ol < 0 ? 0 : (ol > T1 ? T1 : ol));
   const int ilen = (int)(il < 0 ? 0 : (il > T2 ? T2 : il));
   uint32_t* bits_s = reinterpret_cast<uint32_t*>(smem + plan.bits_off);
-  uint32_t* bits_g = bits_ws + (kBitsInSmem ? 0 : (size_t)b * T1 * plan.W);
+  uint32_t* bits_g = bits_ws + (kBitsInSmem ? 0 : (size_t)b * T1 * plan.Wb);
   auto put_bits = [&](size_t idx, uint32_t w) {
     if constexpr (kBitsInSmem) bits_s[idx] = w; else bits_g[idx] = w;
   };
@@ -298,7 +387,7 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
   const bool active = (olen > 0 && ilen > 0);
   const int nchunks = active ? (olen + R - 1) / R : 0;
   // only the warps that hold live columns take part in the DP
-  const int Wl = active ? (ilen + 31) / 32 : 0;
+  const int Wl = active ? (ilen + 32 * plan.NC - 1) / (32 * plan.NC) : 0;
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -310,7 +399,7 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
   for (int j = tid; j < T2; j += nthreads) dur_s[j] = 0;
   for (int i = tid; i < (W + 1) * kMasEdge; i += nthreads) reinterpret_cast<uint32_t*>(edge)[i] = kMasSentinel;
   if (active)
-    for (int j = tid; j < W; j += nthreads) put_bits(j, 0u);   // row 0 carries no decisions
+    for (int j = tid; j < plan.Wb; j += nthreads) put_bits(j, 0u);   // row 0 carries no decisions
   __syncthreads();
 
   const size_t slab = (size_t)b * T1 * T2;
@@ -346,12 +435,21 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
   } else if (warp < W) {
     // ------------------------------ DP warps (skewed wavefront) ------------------------------
     if (warp < Wl) {
-      if (warp == 0)
-        dp_warp<kBitsInSmem, true>(full, empty, edge, ring, bits_s, bits_g, plan, slab, T2, olen, nchunks, warp, lane,
-                                   b == 0 && warp == Wl - 1);
-      else
-        dp_warp<kBitsInSmem, false>(full, empty, edge, ring, bits_s, bits_g, plan, slab, T2, olen, nchunks, warp, lane,
-                                    b == 0 && warp == Wl - 1);
+      auto run = [&](auto nc_tag) {
+        constexpr int kNC = decltype(nc_tag)::value;
+        if (warp == 0)
+          dp_warp<kBitsInSmem, true, kNC>(full, empty, edge, ring, bits_s, bits_g, plan, slab, T2, olen, nchunks, warp,
+                                          lane, b == 0 && warp == Wl - 1);
+        else
+          dp_warp<kBitsInSmem, false, kNC>(full, empty, edge, ring, bits_s, bits_g, plan, slab, T2, olen, nchunks, warp,
+                                           lane, b == 0 && warp == Wl - 1);
+      };
+      switch (plan.NC) {
+        case 1: run(std::integral_constant<int, 1>{}); break;
+        case 2: run(std::integral_constant<int, 2>{}); break;
+        case 3: run(std::integral_constant<int, 3>{}); break;
+        default: run(std::integral_constant<int, 4>{}); break;
+      }
       if (b == 0 && tid == 0) { g_mas_timeline[1] = gtime(); g_mas_timeline[7] = (unsigned long long)clock64(); }
     }
   } else {
@@ -370,8 +468,8 @@ mas_kernel(const float* __restrict__ logp, const int64_t* __restrict__ in_lens, 
       uint32_t win = 0;                                // bit 31 <-> column j, bit k <-> column j - 31 + k
       if (row >= 1) {
         const int wj = j >> 5;
-        const uint32_t hi = get_bits((size_t)row * W + wj);
-        const uint32_t lo = wj > 0 ? get_bits((size_t)row * W + wj - 1) : 0u;
+        const uint32_t hi = get_bits((size_t)row * plan.Wb + wj);
+        const uint32_t lo = wj > 0 ? get_bits((size_t)row * plan.Wb + wj - 1) : 0u;
         const unsigned long long x = ((unsigned long long)hi << 32) | lo;
         win = (uint32_t)(x >> ((j & 31) + 1));
       }

@@ -13,5 +13,6 @@ for (B, T1, T2) in [(64, 2000, 300), (64, 800, 150), (64, 2000, 30), (64, 2000, 
     t = list(buf)
     print("   DP: %d cycles in %d ns -> %.0f MHz, %.1f cycles/row" % (t[7]-t[6], t[1]-t[0], (t[7]-t[6])/max(t[1]-t[0],1)*1e3, (t[7]-t[6])/T1))
     n=max(t[11],1); print("   last DP warp, cycles per chunk of %d rows: wait %.0f rows %.0f (%d chunks)" % (t[12], t[8]/n, t[9]/n, n))
+    print("   warp 0 rows-phase cycles per chunk %.0f; last-warp group-wait spins per chunk %.2f" % (t[13]/n, t[14]/n))
     print((B, T1, T2), "dp0 %.1f us | all dp+fill %.1f | fill %.1f | backtrack %.1f | scatter %.1f" % (
         (t[1]-t[0])/1e3, (t[2]-t[0])/1e3, (t[5]-t[0])/1e3, (t[3]-t[2])/1e3, (t[4]-t[3])/1e3))
