@@ -187,7 +187,9 @@ struct PrepConvParams {
 };
 template <typename T>
 __global__ void __launch_bounds__(256) prep_convs_kernel(const PrepConvParams p) {
-  extern __shared__ float tile[];                  // [k][32][65]
+  extern __shared__ float tile[];                  // [k][32][65], tap planes kPlane apart (odd mod 32: the staging
+                                                   // loop walks taps fastest and would hit one bank k times otherwise)
+  constexpr int kPlane = 32 * 65 + 7;
   const PrepConvItem& it = p.it[blockIdx.z];
   const int k = it.k, N = p.N, C = p.C;
   const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
@@ -197,21 +199,21 @@ __global__ void __launch_bounds__(256) prep_convs_kernel(const PrepConvParams p)
     const int c = r / k, t = r - c * k;
     float v = 0.f;
     if (n0 + n < N && c0 + c < C) v = it.v[((size_t)(n0 + n) * C + c0 + c) * k + t] * it.scale[n0 + n];
-    tile[(t * 32 + n) * 65 + c] = v;
+    tile[t * kPlane + n * 65 + c] = v;
   }
   __syncthreads();
   T* dst = reinterpret_cast<T*>(it.dst);
   const size_t ldw = (size_t)k * C;
   for (int idx = threadIdx.x; idx < k * 32 * 64; idx += 256) {
     const int c = idx & 63, n = (idx >> 6) & 31, t = idx >> 11;
-    if (n0 + n < N && c0 + c < C) put(dst + (size_t)(n0 + n) * ldw + (size_t)t * C + c0 + c, tile[(t * 32 + n) * 65 + c]);
+    if (n0 + n < N && c0 + c < C) put(dst + (size_t)(n0 + n) * ldw + (size_t)t * C + c0 + c, tile[t * kPlane + n * 65 + c]);
   }
   if (it.dstT) {
     T* dstT = reinterpret_cast<T*>(it.dstT);
     for (int idx = threadIdx.x; idx < k * 64 * 32; idx += 256) {
       const int n = idx & 31, c = (idx >> 5) & 63, t = idx >> 11;
       if (n0 + n < N && c0 + c < C)
-        put(dstT + (size_t)(c0 + c) * it.lddT + it.dcolT + (size_t)t * N + n0 + n, tile[(t * 32 + n) * 65 + c]);
+        put(dstT + (size_t)(c0 + c) * it.lddT + it.dcolT + (size_t)t * N + n0 + n, tile[t * kPlane + n * 65 + c]);
     }
   }
 }
@@ -348,7 +350,7 @@ static int prepare_impl(const radtts_flow_dims& d, const radtts_flow_weights& w,
       if (want_backward) { r.dstT = base + L.w_dg[i]; r.lddT = L.dg_k[i]; r.dcolT = 0; }
     }
     // two launches (k taps / 1 tap) so that the 1x1 items do not pay for the k-tap tile
-    const size_t smem_k = (size_t)k * 32 * 65 * sizeof(float), smem_1 = (size_t)32 * 65 * sizeof(float);
+    const size_t smem_k = (size_t)k * (32 * 65 + 7) * sizeof(float), smem_1 = (size_t)(32 * 65 + 7) * sizeof(float);
     if (smem_k > 48 * 1024) return RADTTS_ERR_UNSUPPORTED;
     prep_convs_kernel<T><<<dim3(ceil_div(nc, 32), ceil_div(nc, 64), nl), 256, smem_k, st>>>(pp);
     RB_TRY(after_launch());

@@ -53,15 +53,24 @@ invconv_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, in
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
     const float* xr = xs + (size_t)(4 * rg) * zld;
-#pragma unroll 4
-    for (int j = 0; j < zld; ++j) {
-      const float4 w4 = *reinterpret_cast<const float4*>(wt + (size_t)j * zld + 4 * cg);
-      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+    // four input channels per step: the x values come as one broadcast LDS.128 per row instead of four scalar loads
+    // (the loop is bound by shared-memory wavefronts, not by FMAs)
+#pragma unroll 2
+    for (int j = 0; j < zld; j += 4) {
+      float xv[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float xv = xr[(size_t)i * zld + j];
+        const float4 t = *reinterpret_cast<const float4*>(xr + (size_t)i * zld + j);
+        xv[i][0] = t.x; xv[i][1] = t.y; xv[i][2] = t.z; xv[i][3] = t.w;
+      }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(wv[k], xv, acc[i][k]);
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wt + (size_t)(j + jj) * zld + 4 * cg);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(wv[k], xv[i][jj], acc[i][k]);
       }
     }
 #pragma unroll

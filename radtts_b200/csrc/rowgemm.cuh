@@ -234,10 +234,71 @@ struct EpiCoupling {
   RowMeta meta;
   __device__ __forceinline__ RowState prep(int row) const { return RowState{meta.valid(row), 1.f}; }
   __device__ __forceinline__ const float* colvec() const { return bias; }
+  __device__ __forceinline__ void scale_of(float x, float& s, float& lsv) const {
+    if (scaling == 0) { s = (tanhf(x) + 1.f) + 1e-6f; lsv = logf(s); }
+    else if (scaling == 1) { s = expf(x); lsv = x; }
+    else if (scaling == 2) { s = 1.f / (1.f + expf(-(x + 10.f))) + 1e-6f; lsv = logf(s); }
+    else { s = 1.f; lsv = 0.f; }
+  }
   template <int W>
   __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
                                              const float (&cv)[W]) const {
     const bool ok = rs.ok;
+    constexpr int NP = W / 2;                 // channel pairs in this chunk
+    const int c0 = col0 >> 1;
+    const size_t zi0 = (size_t)row * zld + c_off + h + c0;
+    // A thread owns one row and W consecutive columns: its outputs are contiguous runs (W floats of params, W/2 of z
+    // and of log_s).  Written as 16-byte vectors where the run is whole and aligned -- as scalars every warp-wide store
+    // touched 32 different rows, one sector each, and the 160-wide `end` GEMM spent most of its time in this epilogue.
+    if (NP % 4 == 0 && c0 + NP <= h) {
+      const bool zvec = ((c_off + h + c0) & 3) == 0;   // the z columns start at c_off + h: aligned for some flows only
+      float z1[NP], outv[NP], ls[NP], pv[W];
+      if (ok) {
+        if (zvec) {
+#pragma unroll
+          for (int i = 0; i < NP; i += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(zsrc + zi0 + i);
+            z1[i] = t.x; z1[i + 1] = t.y; z1[i + 2] = t.z; z1[i + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NP; ++i) z1[i] = zsrc[zi0 + i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const float x = acc[2 * i] + cv[2 * i];
+        const float b = acc[2 * i + 1] + cv[2 * i + 1];
+        outv[i] = 0.f; ls[i] = 0.f;
+        if (ok) {
+          float sc, lsv;
+          scale_of(x, sc, lsv);
+          if (inverse) outv[i] = (z1[i] - b) / sc;
+          else { outv[i] = sc * z1[i] + b; ls[i] = lsv; }
+        }
+        pv[2 * i] = ok ? x : 0.f;
+        pv[2 * i + 1] = ok ? b : 0.f;
+      }
+      if (zvec) {
+#pragma unroll
+        for (int i = 0; i < NP; i += 4)
+          *reinterpret_cast<float4*>(zdst + zi0 + i) = make_float4(outv[i], outv[i + 1], outv[i + 2], outv[i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) zdst[zi0 + i] = outv[i];
+      }
+      if (log_s) {
+#pragma unroll
+        for (int i = 0; i < NP; i += 4)
+          *reinterpret_cast<float4*>(log_s + (size_t)row * (zld / 2) + c0 + i) = make_float4(ls[i], ls[i + 1], ls[i + 2], ls[i + 3]);
+      }
+      if (params) {
+#pragma unroll
+        for (int i = 0; i < W; i += 4)
+          *reinterpret_cast<float4*>(params + (size_t)row * zld + col0 + i) = make_float4(pv[i], pv[i + 1], pv[i + 2], pv[i + 3]);
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < W; i += 2) {
       const int c = (col0 + i) >> 1;
@@ -247,14 +308,11 @@ struct EpiCoupling {
       const size_t zi = (size_t)row * zld + c_off + h + c;
       float outv = 0.f, ls = 0.f;
       if (ok) {
-        float s, lsv;
-        if (scaling == 0) { s = (tanhf(x) + 1.f) + 1e-6f; lsv = logf(s); }
-        else if (scaling == 1) { s = expf(x); lsv = x; }
-        else if (scaling == 2) { s = 1.f / (1.f + expf(-(x + 10.f))) + 1e-6f; lsv = logf(s); }
-        else { s = 1.f; lsv = 0.f; }
+        float sc, lsv;
+        scale_of(x, sc, lsv);
         const float z1 = zsrc[zi];
-        if (inverse) outv = (z1 - b) / s;
-        else { outv = s * z1 + b; ls = lsv; }
+        if (inverse) outv = (z1 - b) / sc;
+        else { outv = sc * z1 + b; ls = lsv; }
       }
       zdst[zi] = outv;
       if (log_s) log_s[(size_t)row * (zld / 2) + c] = ls;
