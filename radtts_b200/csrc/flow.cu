@@ -383,6 +383,25 @@ static int prepare_impl(const radtts_flow_dims& d, const radtts_flow_weights& w,
 // ====================================================================================================
 // forward / inverse
 // ====================================================================================================
+// One internal side stream (+ fork / join events) per process, created on first use -- i.e. during the eager warm-up
+// that precedes any stream capture.
+struct SideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork[RADTTS_MAX_LAYERS];
+  cudaEvent_t join;
+};
+static SideStream* side_stream() {
+  static SideStream s{};
+  static int state = 0;   // 0 = not created, 1 = ok, -1 = failed
+  if (state == 0) {
+    bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < RADTTS_MAX_LAYERS; ++i) ok = cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+    state = ok ? 1 : -1;
+  }
+  return state == 1 ? &s : nullptr;
+}
+
 template <typename T>
 static int wn_and_coupling(const radtts_flow_dims& d, const uint8_t* base, const FlowLayout& L, const PlanView& pv,
                            const radtts_flow_buffers& buf, int inverse, cudaStream_t st) {
@@ -403,6 +422,11 @@ static int wn_and_coupling(const radtts_flow_dims& d, const uint8_t* base, const
     EpiBiasAct<T, ACT_NONE> e{x, nc, 0, reinterpret_cast<const float*>(base + L.b_start), meta, ACT_NONE, 0, 0, k, 1};
     RB_TRY((run_gemm<T>(g, e, st)));
   }
+  // res_skip(i) and in_layer(i + 1) both only READ x_{i+1} and write disjoint buffers: res_skip goes to a side stream
+  // (fork / join with events -- also what a stream capture records), so its CTAs back-fill the SMs that the in_layer
+  // GEMM leaves idle in its last wave (340 tiles on 148 SMs = 2.3 waves) instead of waiting for it to drain.
+  SideStream* side = side_stream();
+  if (!side) return RADTTS_ERR_UNSUPPORTED;
   for (int i = 0; i < nl; ++i) {
     T* xi = x + (size_t)i * rows * nc;
     T* xo = x + (size_t)(i + 1) * rows * nc;
@@ -414,15 +438,20 @@ static int wn_and_coupling(const radtts_flow_dims& d, const uint8_t* base, const
                                     d.partial_padding, i, k, 1};
       RB_TRY((run_gemm<T>(g, e, st)));
     }
-    g.nseg = 1;
-    g.seg[0] = Seg{xo, nc, 0, 0, nc};
-    g.w = base + L.w_rs[i]; g.ldw = nc; g.N = nc;
+    RB_CUDA(cudaEventRecord(side->fork[i], st));
+    RB_CUDA(cudaStreamWaitEvent(side->stream, side->fork[i], 0));
+    GemmDesc gr = g;
+    gr.nseg = 1;
+    gr.seg[0] = Seg{xo, nc, 0, 0, nc};
+    gr.w = base + L.w_rs[i]; gr.ldw = nc; gr.N = nc;
     {
       EpiBiasAct<T, ACT_SOFTPLUS> e{r, nl * nc, i * nc, reinterpret_cast<const float*>(base + L.b_rs[i]), meta, ACT_SOFTPLUS,
                                     0, 0, k, 1};
-      RB_TRY((run_gemm<T>(g, e, st)));
+      RB_TRY((run_gemm<T>(gr, e, side->stream)));
     }
   }
+  RB_CUDA(cudaEventRecord(side->join, side->stream));
+  RB_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   g.nseg = 1;
   g.seg[0] = Seg{r, nl * nc, 0, 0, nl * nc};
   g.w = base + L.w_end; g.ldw = nl * nc; g.N = d.z_ld;

@@ -13,6 +13,20 @@ MAX_B = 32
 MAX_H = 592
 
 
+class _rnn_matmul_precision:
+    """The GEMMs around the recurrence (input projection, weight / input gradients) replace work cuDNN's RNN does
+    internally, so in fp32 they follow cuDNN's TF32 switch (torch.backends.cudnn.allow_tf32, default True) rather than
+    the matmul one (default False, which sends them to SIMT sgemm kernels)."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(torch.backends.cudnn.allow_tf32)
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+
 def supported(lstm, x):
     return (x.is_cuda and isinstance(lstm, torch.nn.LSTM) and lstm.bidirectional and lstm.num_layers == 1
             and x.shape[0] <= MAX_B and lstm.hidden_size <= MAX_H and lstm.proj_size == 0)
@@ -37,8 +51,9 @@ class _BiLSTMFn(torch.autograd.Function):
         dev = x_tm.device
         need_bwd = any(ctx.needs_input_grad)
         # input projection for every step: one GEMM per direction (plain library GEMM; autocast-aware)
-        gx = (torch.matmul(x_tm.reshape(1, T * B, -1), w_ih.transpose(1, 2)).float()
-              + bias.float()[:, None, :]).reshape(2, T, B, 4 * H).contiguous()
+        with _rnn_matmul_precision():
+            gx = (torch.matmul(x_tm.reshape(1, T * B, -1), w_ih.transpose(1, 2)).float()
+                  + bias.float()[:, None, :]).reshape(2, T, B, 4 * H).contiguous()
         whh = w_hh.detach().float().contiguous()
         h_all = torch.empty((T, B, 2 * H), dtype=torch.float32, device=dev)
         gates = torch.empty((2, T, B, 4 * H), dtype=torch.float32, device=dev) if need_bwd else None
@@ -75,13 +90,14 @@ class _BiLSTMFn(torch.autograd.Function):
         dg2 = dg.reshape(2, T * B, 4 * H)
         dgm = dg2.to(mm)
         xf = x_tm.reshape(T * B, -1).to(mm)
-        d_x = torch.matmul(dgm, w_ih.to(mm)).float().sum(0).reshape(x_tm.shape).to(x_tm.dtype)
-        d_w_ih = torch.matmul(dgm.transpose(1, 2), xf).float()
         # h_{t-1} in each direction's own time order
         zeros = torch.zeros((1, B, H), dtype=torch.float32, device=dev)
         h_prev_f = torch.cat((zeros, h_all[:-1, :, :H]), 0).reshape(T * B, H).to(mm)
         h_prev_r = torch.cat((h_all[1:, :, H:], zeros), 0).reshape(T * B, H).to(mm)
-        d_w_hh = torch.stack((dgm[0].t() @ h_prev_f, dgm[1].t() @ h_prev_r)).float()
+        with _rnn_matmul_precision():
+            d_x = torch.matmul(dgm, w_ih.to(mm)).float().sum(0).reshape(x_tm.shape).to(x_tm.dtype)
+            d_w_ih = torch.matmul(dgm.transpose(1, 2), xf).float()
+            d_w_hh = torch.stack((dgm[0].t() @ h_prev_f, dgm[1].t() @ h_prev_r)).float()
         d_bias = dg2.sum(1)
         return d_x, None, d_w_ih.to(w_ih.dtype), d_w_hh, d_bias
 
