@@ -383,25 +383,6 @@ static int prepare_impl(const radtts_flow_dims& d, const radtts_flow_weights& w,
 // ====================================================================================================
 // forward / inverse
 // ====================================================================================================
-// One internal side stream (+ fork / join events) per process, created on first use -- i.e. during the eager warm-up
-// that precedes any stream capture.
-struct SideStream {
-  cudaStream_t stream;
-  cudaEvent_t fork[RADTTS_MAX_LAYERS];
-  cudaEvent_t join;
-};
-static SideStream* side_stream() {
-  static SideStream s{};
-  static int state = 0;   // 0 = not created, 1 = ok, -1 = failed
-  if (state == 0) {
-    bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; ok && i < RADTTS_MAX_LAYERS; ++i) ok = cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
-    state = ok ? 1 : -1;
-  }
-  return state == 1 ? &s : nullptr;
-}
-
 template <typename T>
 static int wn_and_coupling(const radtts_flow_dims& d, const uint8_t* base, const FlowLayout& L, const PlanView& pv,
                            const radtts_flow_buffers& buf, int inverse, cudaStream_t st) {

@@ -33,4 +33,25 @@ inline int check_dims(const radtts_flow_dims* d) {
   return 0;
 }
 
+// One internal side stream (+ fork / join events) per process, created on first use -- i.e. during the eager warm-up
+// that precedes any stream capture.
+constexpr int kSideForks = RADTTS_MAX_LAYERS + 4;
+struct SideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork[kSideForks];
+  cudaEvent_t join;
+};
+inline SideStream* side_stream() {
+  static SideStream s{};
+  static int state = 0;   // 0 = not created, 1 = ok, -1 = failed
+  if (state == 0) {
+    bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < kSideForks; ++i) ok = cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+    state = ok ? 1 : -1;
+  }
+  return state == 1 ? &s : nullptr;
+}
+
+
 }  // namespace rb

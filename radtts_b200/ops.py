@@ -406,18 +406,19 @@ def ctx_ld_of(n_ctx):
     return (n_ctx + 63) // 64 * 64
 
 
-_blob_cache = {}
-
-
 def _cached_blob(flow, dims, prec, inverse, device):
-    key = (id(flow), prec, bool(inverse), dims.c_off, device.index)
-    versions = tuple(p._version for p in flow.parameters())
-    hit = _blob_cache.get(key)
+    """Prepared-weight blob of a frozen flow (inference).  The cache lives ON the module (so it dies with it -- a global
+    dict keyed by id(flow) can hand a new model the blob of a garbage-collected one) and is invalidated by the
+    parameters' version counters."""
+    cache = flow.__dict__.setdefault("_radtts_b200_blobs", {})
+    key = (prec, bool(inverse), dims.c_off, device.index)
+    versions = tuple((id(p), p._version) for p in flow.parameters())
+    hit = cache.get(key)
     if hit is not None and hit[0] == versions:
         return hit[1]
     with torch.no_grad():
         blob = prepare_flow(dims, _flow_weight_list(flow, inverse), prec, False, device)
-    _blob_cache[key] = (versions, blob)
+    cache[key] = (versions, blob)
     return blob
 
 
@@ -552,14 +553,15 @@ def wn_forward(wn, z, context, seq_lens):
     raise NotImplementedError("WN runs fused inside FlowStep (ops.flow_step); standalone WN.forward is not exposed")
 
 
-_conv_cache = {}
-
-
 def _prepared_conv(conv, c_in_pad, prec):
-    """Re-laid-out weight blob of a Conv1d (cached per parameter version: inference weights are frozen)."""
+    """Re-laid-out weight blob of a Conv1d, cached ON the module per parameter version (inference weights are frozen).
+    Not a global dict keyed by id(conv): ids are reused after garbage collection and equal version counters would then
+    hand a new model another model's weights."""
     w, b = conv.weight, conv.bias
-    key = (id(conv), w._version, None if b is None else b._version, c_in_pad, prec, w.device.index)
-    hit = _conv_cache.get(id(conv))
+    cache = conv.__dict__.setdefault("_radtts_b200_blobs", {})
+    slot = (c_in_pad, prec, w.device.index)
+    key = (id(w), w._version, None if b is None else (id(b), b._version))
+    hit = cache.get(slot)
     if hit is not None and hit[0] == key:
         return hit[1]
     L = _lib.lib()
@@ -570,7 +572,7 @@ def _prepared_conv(conv, c_in_pad, prec):
     bf = None if b is None else b.detach().float().contiguous()
     _lib.check(L.radtts_conv_prepare(_lib.ptr(wf), _lib.ptr(bf), c_out, c_in, c_in_pad, k, prec, _lib.ptr(blob),
                                      ctypes.c_size_t(nbytes), _lib.stream_of(w)), "radtts_conv_prepare")
-    _conv_cache[id(conv)] = (key, blob)
+    cache[slot] = (key, blob)
     return blob
 
 
