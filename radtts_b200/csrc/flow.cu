@@ -185,13 +185,15 @@ struct PrepConvParams {
   PrepConvItem it[2 * RADTTS_MAX_LAYERS];
   int N, C;
 };
-template <typename T>
+// K = tap count as a template parameter: the index arithmetic below divides by it ~40 times per thread
+template <typename T, int K>
 __global__ void __launch_bounds__(256) prep_convs_kernel(const PrepConvParams p) {
   extern __shared__ float tile[];                  // [k][32][65], tap planes kPlane apart (odd mod 32: the staging
                                                    // loop walks taps fastest and would hit one bank k times otherwise)
   constexpr int kPlane = 32 * 65 + 7;
   const PrepConvItem& it = p.it[blockIdx.z];
-  const int k = it.k, N = p.N, C = p.C;
+  constexpr int k = K;
+  const int N = p.N, C = p.C;
   const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
   const int per_row = 64 * k;
   for (int idx = threadIdx.x; idx < 32 * per_row; idx += 256) {
@@ -352,12 +354,16 @@ static int prepare_impl(const radtts_flow_dims& d, const radtts_flow_weights& w,
     // two launches (k taps / 1 tap) so that the 1x1 items do not pay for the k-tap tile
     const size_t smem_k = (size_t)k * (32 * 65 + 7) * sizeof(float), smem_1 = (size_t)(32 * 65 + 7) * sizeof(float);
     if (smem_k > 48 * 1024) return RADTTS_ERR_UNSUPPORTED;
-    prep_convs_kernel<T><<<dim3(ceil_div(nc, 32), ceil_div(nc, 64), nl), 256, smem_k, st>>>(pp);
+    if (k == 5) prep_convs_kernel<T, 5><<<dim3(ceil_div(nc, 32), ceil_div(nc, 64), nl), 256, smem_k, st>>>(pp);
+    else if (k == 3) prep_convs_kernel<T, 3><<<dim3(ceil_div(nc, 32), ceil_div(nc, 64), nl), 256, smem_k, st>>>(pp);
+    else if (k == 1) prep_convs_kernel<T, 1><<<dim3(ceil_div(nc, 32), ceil_div(nc, 64), nl), 256, smem_k, st>>>(pp);
+    else if (k == 7) prep_convs_kernel<T, 7><<<dim3(ceil_div(nc, 32), ceil_div(nc, 64), nl), 256, smem_k, st>>>(pp);
+    else return RADTTS_ERR_UNSUPPORTED;
     RB_TRY(after_launch());
     PrepConvParams pr{};
     pr.N = nc; pr.C = nc;
     for (int i = 0; i < nl; ++i) pr.it[i] = pp.it[nl + i];
-    prep_convs_kernel<T><<<dim3(ceil_div(nc, 32), ceil_div(nc, 64), nl), 256, smem_1, st>>>(pr);
+    prep_convs_kernel<T, 1><<<dim3(ceil_div(nc, 32), ceil_div(nc, 64), nl), 256, smem_1, st>>>(pr);
     RB_TRY(after_launch());
   }
   prep_end_kernel<T><<<grid_for((size_t)d.z_ld * nl * nc), 256, 0, st>>>(
@@ -569,8 +575,6 @@ static int wn_layer_impl(const radtts_flow_dims& d, const uint8_t* base, const P
   g.plan = pv.hdr();
   g.nseg = k;
   for (int t = 0; t < k; ++t) g.seg[t] = Seg{x + (size_t)layer * rows * nc, nc, (t - k / 2) << layer, 0, nc};
-  static const int dbg_nseg = [] { const char* e = getenv("RADTTS_DEBUG_NSEG"); return e ? atoi(e) : 0; }();
-  if (dbg_nseg > 0 && dbg_nseg < k) g.nseg = dbg_nseg;   // profiling experiment: shorter K
   g.w = base + L.w_in[layer]; g.ldw = k * nc; g.N = nc;
   EpiBiasAct<T, ACT_SOFTPLUS> e{x + (size_t)(layer + 1) * rows * nc, nc, 0,
                                 reinterpret_cast<const float*>(base + L.b_in[layer]), meta, ACT_SOFTPLUS, d.partial_padding,

@@ -44,7 +44,6 @@ struct TcParams {
   int bn;         // tile width (multiple of 16, <= 256); N is covered by ceil(N / bn) tiles
   int n_tiles_n;
   int rows_alloc;
-  int debug;      // RADTTS_TC_DEBUG bit 0: skip the epilogue functor, bit 1: also skip the TMEM loads (profiling experiments)
   const int* plan;
 };
 
@@ -233,7 +232,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c = g * 64 + q * 16;
-          if (c < p.bn && n0 + c < p.N && !(p.debug & 1)) {
+          if (c < p.bn && n0 + c < p.N) {
             float v[16], cvr[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(src[q][i]);
@@ -246,8 +245,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
           }
         }
       };
-      if (!(p.debug & 2)) load_group(ra, 0);
-      for (int g = 0; g < ngroups && !(p.debug & 2); g += 2) {
+      load_group(ra, 0);
+      for (int g = 0; g < ngroups; g += 2) {
         tmem_ld_wait();
         if (g + 1 < ngroups) load_group(rbuf, g + 1);
         run_group(ra, g);
@@ -278,8 +277,6 @@ inline int launch_rowgemm_tc(const GemmDesc& d, const Epi& epi, cudaStream_t str
   p.N = d.N;
   p.rows_alloc = d.rows_alloc;
   p.plan = d.plan;
-  static const int dbg = [] { const char* e = getenv("RADTTS_TC_DEBUG"); return e ? atoi(e) : 0; }();
-  p.debug = dbg;
   if (d.N % 16) return RADTTS_ERR_INVALID_ARG;
   p.bn = d.N <= kTcMaxBN ? d.N : kTcMaxBN;
   p.n_tiles_n = ceil_div(d.N, p.bn);  // a partial last tile reads zero-filled weight rows and is masked on store

@@ -27,7 +27,7 @@ struct WgTcProb {
 struct WgTcParams {
   CUtensorMap maps[kWgMaxMaps];
   WgTcProb prob[kWgMaxProbs];
-  int nprob, total_tiles, rows_alloc, desc_swap;
+  int nprob, total_tiles, rows_alloc, pad_;
   const int* plan;
 };
 
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t idesc = umma_idesc_bf16(kWgBM, kWgBN, 1, 1);
-      const uint32_t lbo = p.desc_swap ? 1024u : 8192u, sbo = p.desc_swap ? 8192u : 1024u;
+      const uint32_t lbo = 8192u, sbo = 1024u;   // MN-major SW128: 8 KB between 64-channel blocks, 1 KB between 8-row groups
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -192,8 +192,6 @@ struct WgradBatch {
     if (params.nprob == 0) return 0;
     params.plan = plan;
     params.rows_alloc = rows_alloc;
-    static const int swap = [] { const char* e = getenv("RADTTS_WGRAD_DESC_SWAP"); return e ? atoi(e) : 0; }();
-    params.desc_swap = swap;
     static bool configured = false;
     if (!configured) {
       RB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
