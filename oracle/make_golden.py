@@ -198,6 +198,25 @@ def gen_bgap(ns):
         g[name + "_log_det_W"] = np.array([float(v) for v in out["log_det_W_list"]], dtype=np.float32)
         for i, ls in enumerate(out["log_s_list"]):
             g[name + "_log_s_%d" % i] = ls.numpy()
+        # training direction: gradients of a flow-loss-like scalar through the reference's autograd
+        mod.zero_grad()
+        xg = x.clone().requires_grad_(True)
+        tg = txt.clone().requires_grad_(True)
+        out = mod(tg, spk, xg, lens)
+        loss = 0.5 * (out["z"] ** 2).sum() - sum(ls.sum() for ls in out["log_s_list"]) \
+            - 7.0 * sum(out["log_det_W_list"])
+        loss.backward()
+        g[name + "_train_loss"] = np.array(float(loss), dtype=np.float64)
+        g[name + "_g_x"] = xg.grad.numpy()
+        g[name + "_g_txt_summary"], g[name + "_g_txt_sample"] = _param_summary(tg.grad)
+        names = []
+        for pn, prm in mod.named_parameters():
+            if prm.grad is None:
+                continue
+            names.append(pn)
+            g["%s_gp_%d_summary" % (name, len(names) - 1)], g["%s_gp_%d_sample" % (name, len(names) - 1)] = \
+                _param_summary(prm.grad)
+        g[name + "_gp_names"] = np.array(names)
     np.savez_compressed(os.path.join(GOLD, "bgap.npz"), **g)
     print("wrote bgap.npz", os.path.getsize(os.path.join(GOLD, "bgap.npz")), "bytes")
 

@@ -528,16 +528,112 @@ def decoder_inverse(model, residual, context, out_lens):
 # ------------------------------------------------------------------------------------------------------
 # remaining hot-path entry points (filled in as their kernels land)
 # ------------------------------------------------------------------------------------------------------
-def _no_grad_only(name, *tensors):
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-        raise NotImplementedError("%s: the training (backward) direction of the BGAP attribute flows is not built yet; "
-                                  "run it under torch.no_grad() (inference)" % name)
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+# Training direction of the BGAP attribute flows.  The fused kernels below (csrc/convnet.cu, spline.cu)
+# are forward-only; when a gradient is needed these functions run the same math as differentiable GPU library ops
+# (cuDNN convs, element-wise kernels), so that `config_ljs_bgap` trains end to end on the device.  The tensors are small
+# (B x <=8 channels x T for the flow variables, 33 parameters per transformed scalar): this is not the step's hot path.
+def _scale_and_log(x, scaling):
+    """reference common.py:775-808."""
+    if scaling == "tanh":
+        s = (torch.tanh(x) + 1.0) + 1e-6
+        return s, torch.log(s)
+    if scaling == "exp":
+        return torch.exp(x), x
+    if scaling == "sigmoid":
+        s = torch.sigmoid(x + 10.0) + 1e-6
+        return s, torch.log(s)
+    if scaling == "translate":
+        return torch.ones_like(x), torch.zeros_like(x)
+    raise NotImplementedError("scaling_fn %r" % (scaling,))
+
+
+def _simple_conv_net_autograd(net, x, seq_lens):
+    """SimpleConvNet.forward (reference common.py:503-515) through the ConvNorm / PartialConv1d module mirrors."""
+    mask = None
+    if seq_lens is not None:
+        mask = (torch.arange(x.shape[2], device=x.device)[None, :] < seq_lens.to(x.device)[:, None])[:, None].to(x.dtype)
+    for layer in net.layers:
+        x = torch.relu(layer(x, mask))
+    return net.last_layer(x)
+
+
+def _rq_spline_autograd(x, w_tilde, v_tilde, inverse):
+    """splines.py:221-319 (unbounded piecewise-quadratic transform) without boolean-index gathers: evaluated for every
+    element on a clamped copy of x and selected with torch.where, so there is no host synchronisation and the
+    gradient of elements outside [0, 1) is exactly the identity's."""
+    eps = torch.finfo(x.dtype).eps
+    inside = (x >= 0) & (x < 1)
+    xc = torch.where(inside, x, torch.full_like(x, 0.5))
+    w = torch.softmax(w_tilde, dim=-1)
+    v = torch.exp(v_tilde - v_tilde.max(dim=-1, keepdim=True)[0]) + 1e-8
+    v = v / (((v[..., :-1] + v[..., 1:]) / 2) * w).sum(-1, keepdim=True)
+    wc = torch.cumsum(w, -1)
+    wc = torch.cat((wc[..., :-1], torch.ones_like(wc[..., -1:])), -1)
+    wc0 = torch.nn.functional.pad(wc, (1, 0))
+    cdf = torch.cumsum((v[..., 1:] + v[..., :-1]) / 2 * w, -1)
+    cdf = torch.cat((cdf[..., :-1], torch.ones_like(cdf[..., -1:])), -1)
+    cdf0 = torch.nn.functional.pad(cdf, (1, 0))
+    knots = cdf if inverse else wc
+    idx = torch.searchsorted(knots.detach(), xc.detach().unsqueeze(-1)).clamp(max=w.shape[-1] - 1)
+    take = lambda t, i: torch.gather(t, -1, i).squeeze(-1)
+    w_b, w_lo = take(w, idx), take(wc0, idx)
+    v_b, v_n = take(v, idx), take(v, idx + 1)
+    c_lo = take(cdf0, idx)
+    if not inverse:
+        alpha = (xc - w_lo) / w_b.clamp(min=eps)
+        out = alpha ** 2 / 2 * (v_n - v_b) * w_b + alpha * v_b * w_b + c_lo
+        log_j = torch.lerp(v_b, v_n, alpha).clamp(min=eps).log()
+        out = out.clamp(min=eps, max=1.0 - eps)
+        return torch.where(inside, out, x), torch.where(inside, log_j, torch.zeros_like(log_j))
+    qa = (v_n - v_b) * w_b / 2
+    qb = v_b * w_b
+    qc = c_lo - xc
+    alpha = (-qb + torch.sqrt(qb ** 2 - 4 * qa * qc)) / (2 * qa)
+    out = (alpha * w_b + w_lo).clamp(min=eps, max=1.0 - eps)
+    return torch.where(inside, out, x), None
+
+
+def _spline_coupling_autograd(layer, z, context, inverse, seq_lens):
+    """SplineTransformationLayer.forward, use_quadratic=True (reference common.py:694-743)."""
+    import math
+    b, c, t = z.shape
+    h = layer.half_mel_channels
+    z0, z1 = z[:, :h], z[:, h:]
+    z1 = (z1 - layer.bottom) / (layer.top - layer.bottom) if inverse else (z1 - layer.left) / (layer.right - layer.left)
+    nb = layer.n_bins
+    q = _simple_conv_net_autograd(layer.param_predictor, torch.cat((z0, context), 1), seq_lens)
+    q = q.permute(0, 2, 1).reshape(b * t, h, nb).float()
+    x = z1.permute(0, 2, 1).reshape(b * t, h).float()
+    y, log_j = _rq_spline_autograd(x, q[..., :nb // 2], q[..., nb // 2:], inverse)
+    y = y.reshape(b, t, h).permute(0, 2, 1)
+    if inverse:
+        return torch.cat((z0, y * (layer.right - layer.left) + layer.left), 1)
+    y = y * (layer.top - layer.bottom) + layer.bottom
+    log_s = log_j.sum(1).reshape(b, t)[:, None] + h * (math.log(layer.top - layer.bottom) - math.log(layer.right - layer.left))
+    return torch.cat((z0, y), 1), log_s
+
+
+def _affine_coupling_autograd(layer, z, context, inverse, seq_lens):
+    """AffineTransformationLayer.forward with affine_model='simple_conv' (reference common.py:810-832)."""
+    h = z.shape[1] // 2
+    z0, z1 = z[:, :h], z[:, h:]
+    params = _simple_conv_net_autograd(layer.affine_param_predictor, torch.cat((z0, context), 1), seq_lens)
+    s, log_s = _scale_and_log(params[:, :h], layer.scaling_fn)
+    bias = params[:, h:]
+    if inverse:
+        return torch.cat((z0, (z1 - bias) / s), 1)
+    return torch.cat((z0, s * z1 + bias), 1), log_s
 
 
 def pointwise_conv(z, w):
     """y[b,:,t] = W z[b,:,t] (Invertible1x1Conv / Invertible1x1ConvLUS module API on reference-shaped tensors)."""
     _lib.require_cuda(z, w)
-    _no_grad_only("pointwise_conv", z, w)
+    if _needs_grad(z, w):
+        return torch.matmul(w.float(), z.float())   # differentiable library op (training direction of the attribute flows)
     z = z.float().contiguous()
     w = w.detach().float().contiguous()
     B, C, T = z.shape
@@ -584,7 +680,8 @@ def simple_conv_net(net, x, seq_lens):
     """SimpleConvNet.forward (reference common.py:503-515) on packed rows: n_layers x [ConvNorm (+partial padding) ->
     ReLU] then the 1x1 `last_layer`; every layer is one row-GEMM launch with a fused epilogue."""
     _lib.require_cuda(x)
-    _no_grad_only("SimpleConvNet", x, *net.parameters())
+    if _needs_grad(x, *net.parameters()):
+        return _simple_conv_net_autograd(net, x, seq_lens)
     B, C, T = x.shape
     prec = current_precision()
     act = _act_dtype(prec)
@@ -624,10 +721,11 @@ def affine_coupling(layer, z, context, inverse, seq_lens):
     if layer.affine_model == "wavenet":
         raise NotImplementedError("the WN-based coupling runs fused inside FlowStep (ops.flow_step)")
     _lib.require_cuda(z, context)
-    _no_grad_only("AffineTransformationLayer", z, context)
     scaling = layer.scaling_fn
     if isinstance(scaling, list) or scaling not in _SCALING:
         raise NotImplementedError("per-channel scaling_fn lists are not supported")
+    if _needs_grad(z, context, *layer.affine_param_predictor.parameters()):
+        return _affine_coupling_autograd(layer, z.float(), context.float(), inverse, seq_lens)
     z = z.float().contiguous()
     B, C, T = z.shape
     h = C // 2
@@ -643,7 +741,8 @@ def affine_coupling(layer, z, context, inverse, seq_lens):
 def spline_coupling(layer, z, context, inverse, seq_lens):
     """SplineTransformationLayer.forward with use_quadratic=True (reference common.py:694-743, splines.py:221-319)."""
     _lib.require_cuda(z, context)
-    _no_grad_only("SplineTransformationLayer", z, context)
+    if _needs_grad(z, context, *layer.param_predictor.parameters()):
+        return _spline_coupling_autograd(layer, z.float(), context.float(), inverse, seq_lens)
     z = z.float().contiguous()
     B, C, T = z.shape
     h = layer.half_mel_channels

@@ -78,3 +78,46 @@ def test_cuda_bgap_infer_and_forward_match_reference(gold, model_and_sd, name, c
     for i, ls in enumerate(out["log_s_list"]):
         want = torch.from_numpy(gold[name + "_log_s_%d" % i])
         assert torch.allclose(_valid(ls.cpu(), lc // g), _valid(want, lc // g), rtol=1e-3, atol=2e-4), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["f0", "energy"])
+def test_cuda_bgap_training_direction_gradients_match_reference(gold, model_and_sd, name, cuda_lib):
+    """Training direction of the attribute flows: loss value, input gradients and every parameter
+    gradient against the reference's autograd (golden: oracle/make_golden.py::gen_bgap)."""
+    from radtts_b200 import ops
+    model, _ = model_and_sd
+    mod = getattr(model, name + "_pred_module").cuda()
+    mod.zero_grad()
+    txt = torch.from_numpy(gold["txt"]).cuda().requires_grad_(True)
+    spk = torch.from_numpy(gold["spk"]).cuda()
+    lens = torch.from_numpy(gold["lens"]).cuda()
+    x = torch.from_numpy(gold[name + "_x_in"]).cuda().requires_grad_(True)
+    ops.set_precision("fp32")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out = mod(txt, spk, x, lens)
+        loss = 0.5 * (out["z"] ** 2).sum() - sum(ls.sum() for ls in out["log_s_list"]) - 7.0 * sum(out["log_det_W_list"])
+        loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        ops.set_precision(None)
+    want = float(gold[name + "_train_loss"])
+    assert abs(float(loss) - want) < 1e-4 * abs(want), (float(loss), want)
+    gx = torch.from_numpy(gold[name + "_g_x"])
+    assert torch.allclose(x.grad.cpu(), gx, rtol=2e-3, atol=2e-4), float((x.grad.cpu() - gx).abs().max())
+
+    def check(t, summary, sample, what):
+        f = t.detach().double().flatten().cpu()
+        got = np.array([f.sum().item(), f.norm().item()])
+        assert abs(got[1] - summary[1]) <= 2e-3 * summary[1] + 1e-6, (what, got, summary)
+        assert np.allclose(f[::1009][:64].float().numpy(), sample, rtol=5e-3, atol=1e-4 * max(summary[1], 1e-3)), what
+
+    check(txt.grad, gold[name + "_g_txt_summary"], gold[name + "_g_txt_sample"], "txt")
+    params = dict(mod.named_parameters())
+    for i, pn in enumerate(gold[name + "_gp_names"]):
+        p = params[str(pn)]
+        assert p.grad is not None, pn
+        check(p.grad, gold["%s_gp_%d_summary" % (name, i)], gold["%s_gp_%d_sample" % (name, i)], str(pn))

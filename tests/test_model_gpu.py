@@ -144,3 +144,35 @@ def test_fused_attention_ctc_matches_torch(cuda_lib):
         (gr,) = torch.autograd.grad(lr * 1.7, r)
         assert abs(float(la) - float(lr)) < 1e-4 * abs(float(lr)) + 1e-6, (float(la), float(lr))
         assert torch.allclose(ga, gr, rtol=1e-3, atol=1e-6), float((ga - gr).abs().max())
+
+
+def test_bgap_config_trains_end_to_end(cuda_lib):
+    """config_ljs_bgap (decoder + duration / voicing predictors + BGAP F0 and energy flows): forward, RADTTSLoss with
+    the attribute losses, backward -- every trainable parameter of the attribute flows receives a finite gradient."""
+    torch.manual_seed(0)
+    cfg = configs.model_config("bgap")
+    m = RADTTS(**cfg).train()
+    synth.load_synth(m, seed=1234)
+    m = m.cuda()
+    b = {k: v.cuda() for k, v in synth.synth_batch(2, 64, 18, seed=77, with_attributes=True).items()}
+    crit = rloss.RADTTSLoss(1.0, cfg["n_group_size"], cfg["dur_model_config"], cfg["f0_model_config"],
+                            cfg["energy_model_config"], cfg["v_model_config"], configs.LOSS_WEIGHTS)
+    ops.set_precision("fp32")
+    try:
+        out = m(b["mel"], b["speaker_ids"], b["text"], b["in_lens"], b["out_lens"], binarize_attention=True,
+                attn_prior=b["attn_prior"], f0=b["f0"], energy_avg=b["energy_avg"], voiced_mask=b["voiced_mask"],
+                p_voiced=b["p_voiced"])
+        losses = crit(out, b["in_lens"], b["out_lens"])
+        total = sum(v * w for v, w in losses.values() if w > 0)
+        total.backward()
+    finally:
+        ops.set_precision(None)
+    assert torch.isfinite(total)
+    assert {"loss_f0", "loss_energy"} <= set(losses) or any("f0" in k for k in losses), sorted(losses)
+    for prefix in ("f0_pred_module.", "energy_pred_module."):
+        got = [(n, p.grad) for n, p in m.named_parameters() if n.startswith(prefix) and p.requires_grad]
+        assert got
+        missing = [n for n, g in got if g is None]
+        assert not missing, missing[:5]
+        assert all(bool(torch.isfinite(g).all()) for _, g in got)
+        assert sum(float(g.abs().sum()) for _, g in got) > 0
