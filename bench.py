@@ -208,6 +208,22 @@ def extras(model, batch, peaks):
                                 "what": "8-flow decoder sampling direction (config_ljs_radtts), bf16, batch %d x <=%d frames, "
                                         "conditioning given" % (B, T1),
                                 "frac_of_bf16_burst_peak": round(frames * FLOP_PER_FRAME_FWD / ms / 1e9 / peaks["tf_burst"], 4)}
+        # full RADTTS.infer (reference radtts.py:541-684): text encoder, length regulation by the given durations,
+        # context BiLSTM, 8-flow decoder; durations chosen so that every utterance has exactly out_lens frames
+        try:
+            T2 = batch["text"].shape[1]
+            in_l, out_l = batch["in_lens"].clamp(min=1), batch["out_lens"]
+            base = (out_l // in_l)[:, None].expand(-1, T2)
+            tok = torch.arange(T2, device=dev)[None, :]
+            dur = torch.where(tok < in_l[:, None], base + (tok < (out_l - (out_l // in_l) * in_l)[:, None]).long(),
+                              torch.zeros_like(base))
+            spk = torch.zeros(B, dtype=torch.long, device=dev)
+            ms = _time_ms(lambda: model.infer(spk, batch["text"], 0.8, dur=dur), 3)
+            out["infer_e2e"] = {"value": round(frames / ms * 1e3, 1), "unit": "mel frames/s", "ms": round(ms, 3),
+                                "what": "RADTTS.infer end to end (text -> mel, durations given), bf16, batch %d x <=%d "
+                                        "frames x <=%d tokens; includes a host sync for the output length" % (B, T1, T2)}
+        except Exception as e:   # reported, never required
+            out["infer_e2e"] = {"error": repr(e)[:200]}
     model.train(was_training)
     for (b, t1, t2) in ((B, T1, batch["text"].shape[1]), (64, 2000, 300)):
         gen = torch.Generator(device=dev).manual_seed(0)

@@ -110,6 +110,7 @@ RADTTS_API int radtts_unpack_frames(const float* src, int ld, int col_off, const
  * ---------------------------------------------------------------------------------------------- */
 #define RADTTS_PREC_FP32 0
 #define RADTTS_PREC_BF16 1
+#define RADTTS_PREC_BF16X2 2  /* LSTM recurrence only: operands split into hi + lo bf16 (16 mantissa bits), fp32 accumulate */
 #define RADTTS_MAX_LAYERS 8
 
 typedef struct radtts_flow_dims {
@@ -283,7 +284,9 @@ RADTTS_API int radtts_context_scatter(const float* grad_context, const int32_t* 
  *   backward: dh_all (T, B, 2H) -> dgates_all (2, T, B, 4H) (pre-activation gate gradients).
  *   B <= 32, H <= 592.  ws: radtts_lstm_workspace_bytes(B, H).
  *   precision: RADTTS_PREC_FP32 -- fp32 FMA recurrence; RADTTS_PREC_BF16 (H % 8 == 0, else fp32) -- the recurrent product runs
- *   on tensor cores with bf16 W_hh and bf16 exchanged h / dgates, fp32 accumulate; state, gates and every output fp32.
+ *   on tensor cores with bf16 W_hh and bf16 exchanged h / dgates, fp32 accumulate; state, gates and every output fp32;
+ *   RADTTS_PREC_BF16X2 -- the same with every operand split into hi + lo bf16 parts (3 MMAs, 16 mantissa bits): meant
+ *   for fp32 LSTMs wherever cuDNN itself would be allowed TF32 (10 mantissa bits).
  * ---------------------------------------------------------------------------------------------- */
 RADTTS_API size_t radtts_lstm_workspace_bytes(int B, int H);
 RADTTS_API int radtts_lstm_forward(const float* gx, const float* whh, const int* lens, int T, int B, int H,

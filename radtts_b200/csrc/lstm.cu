@@ -351,6 +351,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits (TF32 keeps 10).  Used by the kSplit = 2 variants,
+// which replace the fp32 FMA recurrence wherever cuDNN itself would be allowed TF32 (torch.backends.cudnn.allow_tf32).
+__device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
+  hi = __bfloat162float(__float2bfloat16(x));
+  lo = x - hi;
+}
+__device__ __forceinline__ void pack_split(float a, float b, uint32_t& hi, uint32_t& lo) {
+  float ah, al, bh, bl;
+  split_bf16(a, ah, al);
+  split_bf16(b, bh, bl);
+  hi = pack_bf16(ah, bh);
+  lo = pack_bf16(al, bl);
+}
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint4& a, const uint2& b) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -360,6 +373,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint4& a, co
 constexpr int kLstmMmaFwdThreads = 128;   // 4 warps = 4 batch n-tiles of 8; each warp: 2 m-tiles x full K
 
 // hbuf (bf16, fragment order): [2 dir][2 ping-pong][KS = H/16][4 n-tiles][32 lanes] uint2
+template <int kSplit>
 __global__ void __launch_bounds__(kLstmMmaFwdThreads, 1)
 lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whh, const int* __restrict__ lens, LstmDims d,
                     float* __restrict__ h_all, float* __restrict__ gates_save, float* __restrict__ c_save,
@@ -369,8 +383,10 @@ lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whh,
   const int KS = (H + 15) / 16;              // K = H padded to 16 with zero weights / zero state
   const int dir = blockIdx.x / d.G, cta = blockIdx.x % d.G;
   const int u0 = cta * 8;
-  uint4* ws = reinterpret_cast<uint4*>(smraw);                       // [2 m-tiles][KS][32]
-  uint2* hs = reinterpret_cast<uint2*>(smraw + (size_t)2 * KS * 32 * sizeof(uint4));   // [KS][4][32]
+  // kSplit == 2: every operand exists twice (hi part, then lo part, same layout): acc += Wh hh + Wh hl + Wl hh
+  uint4* ws = reinterpret_cast<uint4*>(smraw);                       // [kSplit][2 m-tiles][KS][32]
+  uint2* hs = reinterpret_cast<uint2*>(smraw + (size_t)kSplit * 2 * KS * 32 * sizeof(uint4));   // [kSplit][KS][4][32]
+  const size_t ws_part = (size_t)2 * KS * 32, hs_part = (size_t)KS * 4 * 32;
   __shared__ __align__(8) uint64_t bar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
@@ -384,8 +400,13 @@ lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whh,
     const float* r0 = W + (size_t)((2 * mt) * H + u0 + gg) * H;       // row gg   (gate 2 mt)
     const float* r1 = W + (size_t)((2 * mt + 1) * H + u0 + gg) * H;   // row gg+8 (gate 2 mt + 1)
     auto at = [&](const float* r, int kk) { return kk < H ? r[kk] : 0.f; };
-    ws[i] = make_uint4(pack_bf16(at(r0, k), at(r0, k + 1)), pack_bf16(at(r1, k), at(r1, k + 1)),
-                       pack_bf16(at(r0, k + 8), at(r0, k + 9)), pack_bf16(at(r1, k + 8), at(r1, k + 9)));
+    uint4 hi, lo;
+    pack_split(at(r0, k), at(r0, k + 1), hi.x, lo.x);
+    pack_split(at(r1, k), at(r1, k + 1), hi.y, lo.y);
+    pack_split(at(r0, k + 8), at(r0, k + 9), hi.z, lo.z);
+    pack_split(at(r1, k + 8), at(r1, k + 9), hi.w, lo.w);
+    ws[i] = hi;
+    if (kSplit == 2) ws[ws_part + i] = lo;
   }
   const int u = u0 + g;                       // the unit this thread finalises, for batch columns bcol, bcol + 1
   const int bcol = warp * 8 + 2 * q;
@@ -394,7 +415,7 @@ lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whh,
   len_b[1] = bcol + 1 < B ? lens[bcol + 1] : 0;
   float c_state[2] = {0.f, 0.f};
   unsigned phase = 0;
-  const size_t hbytes = (size_t)KS * 4 * 32 * sizeof(uint2);
+  const size_t hbytes = (size_t)kSplit * KS * 4 * 32 * sizeof(uint2);   // hi block, then lo block
   const int KS0 = KS / 2;
   // where (k = u, n = bcol + e) sits in the fragment-ordered exchange buffer (32-bit word index; u even lanes store)
   const int kk = u & 15;
@@ -412,11 +433,16 @@ lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whh,
     uint32_t* hnext = reinterpret_cast<uint32_t*>(hbuf + (size_t)(dir * 2 + ((s + 1) & 1)) * (hbytes / sizeof(uint2)));
     if (tid == 0) {
       asm volatile("fence.proxy.async;" ::: "memory");
-      const uint32_t b0 = (uint32_t)((size_t)KS0 * 4 * 32 * sizeof(uint2)), b1 = (uint32_t)hbytes - b0;
-      mbar_arrive_expect_tx(&bar[0], b0);
-      bulk_g2s(hs, hprev, b0, &bar[0]);
-      mbar_arrive_expect_tx(&bar[1], b1);
-      bulk_g2s(hs + (size_t)KS0 * 4 * 32, hprev + (size_t)KS0 * 4 * 32, b1, &bar[1]);
+      // two copies per operand part: k-steps [0, KS0) and [KS0, KS); bar[0] completes when every first half is in
+      const uint32_t b0 = (uint32_t)((size_t)KS0 * 4 * 32 * sizeof(uint2));
+      const uint32_t b1 = (uint32_t)(hs_part * sizeof(uint2)) - b0;
+      mbar_arrive_expect_tx(&bar[0], b0 * kSplit);
+      mbar_arrive_expect_tx(&bar[1], b1 * kSplit);
+#pragma unroll
+      for (int part = 0; part < kSplit; ++part) {
+        bulk_g2s(hs + part * hs_part, hprev + part * hs_part, b0, &bar[0]);
+        bulk_g2s(hs + part * hs_part + (size_t)KS0 * 4 * 32, hprev + part * hs_part + (size_t)KS0 * 4 * 32, b1, &bar[1]);
+      }
     }
     float gxv[4][2];
 #pragma unroll
@@ -431,20 +457,25 @@ lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whh,
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+    auto mma_step = [&](int ks) {
+      const uint2 bh = hs[((size_t)ks * 4 + warp) * 32 + lane];
+      const uint4 a0 = ws[(size_t)ks * 32 + lane], a1 = ws[((size_t)KS + ks) * 32 + lane];
+      mma_bf16_16816(acc[0][ks & 1], a0, bh);
+      mma_bf16_16816(acc[1][ks & 1], a1, bh);
+      if (kSplit == 2) {
+        const uint2 bl = hs[hs_part + ((size_t)ks * 4 + warp) * 32 + lane];
+        mma_bf16_16816(acc[0][ks & 1], a0, bl);
+        mma_bf16_16816(acc[1][ks & 1], a1, bl);
+        mma_bf16_16816(acc[0][ks & 1], ws[ws_part + (size_t)ks * 32 + lane], bh);
+        mma_bf16_16816(acc[1][ks & 1], ws[ws_part + ((size_t)KS + ks) * 32 + lane], bh);
+      }
+    };
     mbar_wait(&bar[0], (uint32_t)(s & 1));
 #pragma unroll 4
-    for (int ks = 0; ks < KS0; ++ks) {
-      const uint2 bf = hs[((size_t)ks * 4 + warp) * 32 + lane];
-      mma_bf16_16816(acc[0][ks & 1], ws[(size_t)ks * 32 + lane], bf);
-      mma_bf16_16816(acc[1][ks & 1], ws[((size_t)KS + ks) * 32 + lane], bf);
-    }
+    for (int ks = 0; ks < KS0; ++ks) mma_step(ks);
     mbar_wait(&bar[1], (uint32_t)(s & 1));
 #pragma unroll 4
-    for (int ks = KS0; ks < KS; ++ks) {
-      const uint2 bf = hs[((size_t)ks * 4 + warp) * 32 + lane];
-      mma_bf16_16816(acc[0][ks & 1], ws[(size_t)ks * 32 + lane], bf);
-      mma_bf16_16816(acc[1][ks & 1], ws[((size_t)KS + ks) * 32 + lane], bf);
-    }
+    for (int ks = KS0; ks < KS; ++ks) mma_step(ks);
     // C fragment: [0],[1] = (row g, cols 2q, 2q+1), [2],[3] = (row g + 8, cols 2q, 2q+1)
     float hval[2], ig[2], fg[2], gg[2], og[2], cn[2];
 #pragma unroll
@@ -460,7 +491,12 @@ lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whh,
       c_state[e] = cn[e];
       // exchange: units u (even g) and u + 1 (lane + 4) share a 32-bit word
       const float partner = __shfl_down_sync(0xffffffffu, hval[e], 4);
-      if ((g & 1) == 0) hnext[xw[e]] = pack_bf16(hval[e], partner);
+      if ((g & 1) == 0) {
+        uint32_t hi, lo;
+        pack_split(hval[e], partner, hi, lo);
+        hnext[xw[e]] = hi;
+        if (kSplit == 2) hnext[hs_part * 2 + xw[e]] = lo;   // the lo block follows the hi block (hs_part uint2 = 2 words each)
+      }
     }
     asm volatile("fence.proxy.async;" ::: "memory");
     dir_barrier_arrive(counters + dir);
@@ -483,6 +519,7 @@ lstm_fwd_mma_kernel(const float* __restrict__ gx, const float* __restrict__ whh,
 constexpr int kLstmMmaBwdThreads = 256;   // 8 warps split K = 4H; each warp: 2 batch m-tiles x 8 units
 
 // dgbuf (bf16, A-fragment order): [2 dir][2 ping-pong][KS = 4H/16][2 m-tiles][32 lanes] uint4
+template <int kSplit>
 __global__ void __launch_bounds__(kLstmMmaBwdThreads, 1)
 lstm_bwd_mma_kernel(const float* __restrict__ dh_all, const float* __restrict__ whh, const int* __restrict__ lens,
                     const float* __restrict__ gates_save, const float* __restrict__ c_save, LstmDims d,
@@ -492,9 +529,11 @@ lstm_bwd_mma_kernel(const float* __restrict__ dh_all, const float* __restrict__ 
   const int J = 4 * H, KS = J / 16, KSW = (KS + 7) / 8;   // H % 8 == 0 -> J % 16 == 0; warp w owns k-steps [w KSW, ..)
   const int dir = blockIdx.x / d.G, cta = blockIdx.x % d.G;
   const int u0 = cta * 8;
-  uint2* wt = reinterpret_cast<uint2*>(smraw);                                            // [KS][32]  B fragments
-  uint4* dgs = reinterpret_cast<uint4*>(smraw + (size_t)KS * 32 * sizeof(uint2));          // [KS][2][32] A fragments
-  float* red = reinterpret_cast<float*>(smraw + (size_t)KS * 32 * sizeof(uint2) + (size_t)KS * 2 * 32 * sizeof(uint4));
+  // kSplit == 2: hi parts, then lo parts (same layout): acc += Ah Bh + Ah Bl + Al Bh
+  uint2* wt = reinterpret_cast<uint2*>(smraw);                                                     // [kSplit][KS][32]  B fragments
+  uint4* dgs = reinterpret_cast<uint4*>(smraw + (size_t)kSplit * KS * 32 * sizeof(uint2));          // [kSplit][KS][2][32] A fragments
+  float* red = reinterpret_cast<float*>(smraw + (size_t)kSplit * (KS * 32 * sizeof(uint2) + (size_t)KS * 2 * 32 * sizeof(uint4)));
+  const size_t wt_part = (size_t)KS * 32, dg_part = (size_t)KS * 2 * 32;
   __shared__ __align__(8) uint64_t bar[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
@@ -507,7 +546,11 @@ lstm_bwd_mma_kernel(const float* __restrict__ dh_all, const float* __restrict__ 
     const int ln = i & 31, ks = i >> 5;
     const int gg = ln >> 2, qq = ln & 3;
     const float* c = W + (size_t)(ks * 16 + 2 * qq) * H + u0 + gg;     // B[k = j][n = unit gg]
-    wt[i] = make_uint2(pack_bf16(c[0], c[H]), pack_bf16(c[(size_t)8 * H], c[(size_t)9 * H]));
+    uint2 hi, lo;
+    pack_split(c[0], c[H], hi.x, lo.x);
+    pack_split(c[(size_t)8 * H], c[(size_t)9 * H], hi.y, lo.y);
+    wt[i] = hi;
+    if (kSplit == 2) wt[wt_part + i] = lo;
   }
   // element-wise owner: unit ul = tid & 7, batch b = tid >> 3
   const int ul = tid & 7, b = tid >> 3;
@@ -516,7 +559,7 @@ lstm_bwd_mma_kernel(const float* __restrict__ dh_all, const float* __restrict__ 
   const int len_b = mine ? lens[b] : 0;
   float dc_state = 0.f;
   unsigned phase = 0;
-  const size_t dwords = (size_t)KS * 2 * 32;          // uint4 per exchange buffer
+  const size_t dwords = (size_t)kSplit * KS * 2 * 32;   // uint4 per exchange buffer (hi block, then lo block)
   // where (m = b, k = gate * H + u) sits in the exchange buffer (32-bit word index, even ul lanes store)
   size_t xw[4];
   {
@@ -543,8 +586,10 @@ lstm_bwd_mma_kernel(const float* __restrict__ dh_all, const float* __restrict__ 
         const int ka = min(w * KSW, KS), kb = min(ka + KSW, KS);
         if (kb > ka) {
           const uint32_t cb = (uint32_t)((size_t)(kb - ka) * 2 * 32 * sizeof(uint4));
-          mbar_arrive_expect_tx(&bar[w], cb);
-          bulk_g2s(dgs + (size_t)ka * 2 * 32, dgnext + (size_t)ka * 2 * 32, cb, &bar[w]);
+          mbar_arrive_expect_tx(&bar[w], cb * kSplit);
+#pragma unroll
+          for (int part = 0; part < kSplit; ++part)
+            bulk_g2s(dgs + part * dg_part + (size_t)ka * 2 * 32, dgnext + part * dg_part + (size_t)ka * 2 * 32, cb, &bar[w]);
         } else {
           mbar_arrive(&bar[w]);
         }
@@ -569,9 +614,17 @@ lstm_bwd_mma_kernel(const float* __restrict__ dh_all, const float* __restrict__ 
     mbar_wait(&bar[warp], (uint32_t)(s & 1));
 #pragma unroll 4
     for (int ks = min(warp * KSW, KS), ke = min(ks + KSW, KS); ks < ke; ++ks) {
-      const uint2 bf = wt[(size_t)ks * 32 + lane];
-      mma_bf16_16816(acc[0], dgs[((size_t)ks * 2) * 32 + lane], bf);
-      mma_bf16_16816(acc[1], dgs[((size_t)ks * 2 + 1) * 32 + lane], bf);
+      const uint2 bh = wt[(size_t)ks * 32 + lane];
+      const uint4 a0 = dgs[((size_t)ks * 2) * 32 + lane], a1 = dgs[((size_t)ks * 2 + 1) * 32 + lane];
+      mma_bf16_16816(acc[0], a0, bh);
+      mma_bf16_16816(acc[1], a1, bh);
+      if (kSplit == 2) {
+        const uint2 bl = wt[wt_part + (size_t)ks * 32 + lane];
+        mma_bf16_16816(acc[0], a0, bl);
+        mma_bf16_16816(acc[1], a1, bl);
+        mma_bf16_16816(acc[0], dgs[dg_part + ((size_t)ks * 2) * 32 + lane], bh);
+        mma_bf16_16816(acc[1], dgs[dg_part + ((size_t)ks * 2 + 1) * 32 + lane], bh);
+      }
     }
     // red[warp][batch][unit]
 #pragma unroll
@@ -598,7 +651,12 @@ lstm_bwd_mma_kernel(const float* __restrict__ dh_all, const float* __restrict__ 
 #pragma unroll
     for (int gate = 0; gate < 4; ++gate) {
       const float partner = __shfl_down_sync(0xffffffffu, d4[gate], 1);   // unit ul + 1 of the same batch row
-      if ((ul & 1) == 0) dgcur[xw[gate]] = pack_bf16(d4[gate], partner);
+      if ((ul & 1) == 0) {
+        uint32_t hi, lo;
+        pack_split(d4[gate], partner, hi, lo);
+        dgcur[xw[gate]] = hi;
+        if (kSplit == 2) dgcur[dg_part * 4 + xw[gate]] = lo;   // lo block: dg_part uint4 = 4 words each further on
+      }
     }
     asm volatile("fence.proxy.async;" ::: "memory");
     dir_barrier_arrive(counters + dir);
@@ -625,42 +683,55 @@ static int lstm_plan(int H, LstmDims* d) {
 using namespace rb;
 
 extern "C" size_t radtts_lstm_workspace_bytes(int B, int H) {
-  // hbuf [2][2][H][32] + dgbuf [2][2][4H][32] + counters (exchange buffers are padded to 32 batch lanes)
+  // hbuf [2][2][Hp][32] + dgbuf [2][2][4 Hp][32] floats + counters (exchange buffers are padded to 32 batch lanes and to a
+  // multiple of 16 units; the bf16 / split-bf16 fragment-ordered exchanges of the tensor-core kernels fit in the same space)
   (void)B;
-  return ((size_t)4 * 32 * H + (size_t)16 * 32 * H) * sizeof(float) + 256;
+  const size_t Hp = (size_t)round_up(H, 16);
+  return ((size_t)4 * 32 * Hp + (size_t)16 * 32 * Hp) * sizeof(float) + 256;
 }
 
-static bool lstm_mma_ok(int H, int precision) { return precision == RADTTS_PREC_BF16 && H % 8 == 0 && H >= 32 && H / 8 <= 74; }
+// precision: RADTTS_PREC_FP32 (exact FMA recurrence), RADTTS_PREC_BF16 (single bf16 operands), RADTTS_PREC_BF16X2 (hi + lo
+// bf16 operands, 16 mantissa bits: for fp32 LSTMs wherever cuDNN would be allowed TF32)
+static int lstm_split(int precision) { return precision == RADTTS_PREC_BF16X2 ? 2 : 1; }
+static bool lstm_mma_ok(int H, int precision) {
+  return (precision == RADTTS_PREC_BF16 || precision == RADTTS_PREC_BF16X2) && H % 8 == 0 && H >= 32 && H / 8 <= 74;
+}
 
 extern "C" int radtts_lstm_forward(const float* gx, const float* whh, const int* lens, int T, int B, int H,
                                    float* h_all, float* gates_save, float* c_save, void* ws, size_t ws_bytes,
                                    int precision, void* stream) {
   if (!gx || !whh || !lens || !h_all || !ws || T <= 0 || B <= 0 || H <= 0) return RADTTS_ERR_INVALID_ARG;
-  if (precision != RADTTS_PREC_FP32 && precision != RADTTS_PREC_BF16) return RADTTS_ERR_INVALID_ARG;
+  if (precision != RADTTS_PREC_FP32 && precision != RADTTS_PREC_BF16 && precision != RADTTS_PREC_BF16X2)
+    return RADTTS_ERR_INVALID_ARG;
   if (B > kLstmMaxB) return RADTTS_ERR_UNSUPPORTED;
   if (ws_bytes < radtts_lstm_workspace_bytes(B, H)) return RADTTS_ERR_WORKSPACE;
   LstmDims d{T, B, H, 0, 0};
   RB_TRY(lstm_plan(H, &d));
   cudaStream_t st = (cudaStream_t)stream;
   float* hbuf = reinterpret_cast<float*>(ws);
-  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * 32 * H * sizeof(float));
-  RB_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)4 * 32 * H * sizeof(float), st));
+  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * 32 * round_up(H, 16) * sizeof(float));
+  RB_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)4 * 32 * round_up(H, 16) * sizeof(float), st));
   RB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
   if (lstm_mma_ok(H, precision)) {
     d.U = 8;
     d.G = H / 8;
     const int KS = (H + 15) / 16;
-    const size_t smem = (size_t)2 * KS * 32 * sizeof(uint4) + (size_t)KS * 4 * 32 * sizeof(uint2);
-    static size_t configured_mma = 0;
-    if (smem > configured_mma) {
-      RB_CUDA(cudaFuncSetAttribute(lstm_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured_mma = smem;
+    const int split = lstm_split(precision);
+    const size_t smem = (size_t)split * ((size_t)2 * KS * 32 * sizeof(uint4) + (size_t)KS * 4 * 32 * sizeof(uint2));
+    if (smem <= (size_t)kSmemBudget) {
+      void* fn = split == 2 ? (void*)lstm_fwd_mma_kernel<2> : (void*)lstm_fwd_mma_kernel<1>;
+      static size_t configured_mma[3] = {0, 0, 0};
+      if (smem > configured_mma[split]) {
+        RB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_mma[split] = smem;
+      }
+      uint2* hb = reinterpret_cast<uint2*>(hbuf);
+      void* args[] = {(void*)&gx, (void*)&whh, (void*)&lens, (void*)&d, (void*)&h_all, (void*)&gates_save,
+                      (void*)&c_save, (void*)&hb, (void*)&counters};
+      RB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(2 * d.G), dim3(kLstmMmaFwdThreads), args, smem, st));
+      return after_launch();
     }
-    uint2* hb = reinterpret_cast<uint2*>(hbuf);
-    void* args[] = {(void*)&gx, (void*)&whh, (void*)&lens, (void*)&d, (void*)&h_all, (void*)&gates_save,
-                    (void*)&c_save, (void*)&hb, (void*)&counters};
-    RB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_fwd_mma_kernel, dim3(2 * d.G), dim3(kLstmMmaFwdThreads), args, smem, st));
-    return after_launch();
+    RB_TRY(lstm_plan(H, &d));   // does not fit: fall through to the FMA kernel
   }
   const int R = 4 * d.U;
   const size_t smem = ((size_t)H * R + (size_t)H * kLstmLd + (size_t)16 * R * kLstmMaxB) * sizeof(float);
@@ -681,32 +752,38 @@ extern "C" int radtts_lstm_backward(const float* dh_all, const float* whh, const
                                     size_t ws_bytes, int precision, void* stream) {
   if (!dh_all || !whh || !lens || !gates_save || !c_save || !dgates_all || !ws || T <= 0 || B <= 0 || H <= 0)
     return RADTTS_ERR_INVALID_ARG;
-  if (precision != RADTTS_PREC_FP32 && precision != RADTTS_PREC_BF16) return RADTTS_ERR_INVALID_ARG;
+  if (precision != RADTTS_PREC_FP32 && precision != RADTTS_PREC_BF16 && precision != RADTTS_PREC_BF16X2)
+    return RADTTS_ERR_INVALID_ARG;
   if (B > kLstmMaxB) return RADTTS_ERR_UNSUPPORTED;
   if (ws_bytes < radtts_lstm_workspace_bytes(B, H)) return RADTTS_ERR_WORKSPACE;
   LstmDims d{T, B, H, 0, 0};
   RB_TRY(lstm_plan(H, &d));
   cudaStream_t st = (cudaStream_t)stream;
-  float* dgbuf = reinterpret_cast<float*>(ws) + (size_t)4 * 32 * H;
-  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * 32 * H * sizeof(float));
-  RB_CUDA(cudaMemsetAsync(dgbuf, 0, (size_t)16 * 32 * H * sizeof(float), st));
+  float* dgbuf = reinterpret_cast<float*>(ws) + (size_t)4 * 32 * round_up(H, 16);
+  unsigned* counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(ws) + (size_t)20 * 32 * round_up(H, 16) * sizeof(float));
+  RB_CUDA(cudaMemsetAsync(dgbuf, 0, (size_t)16 * 32 * round_up(H, 16) * sizeof(float), st));
   RB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
   if (lstm_mma_ok(H, precision)) {
     d.U = 8;
     d.G = H / 8;
     const int KS = 4 * H / 16;
-    const size_t smem = (size_t)KS * 32 * sizeof(uint2) + (size_t)KS * 2 * 32 * sizeof(uint4) + (size_t)8 * 32 * 8 * sizeof(float);
-    if (smem > (size_t)kSmemBudget) return RADTTS_ERR_UNSUPPORTED;
-    static size_t configured_mma = 0;
-    if (smem > configured_mma) {
-      RB_CUDA(cudaFuncSetAttribute(lstm_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured_mma = smem;
+    const int split = lstm_split(precision);
+    const size_t smem = (size_t)split * ((size_t)KS * 32 * sizeof(uint2) + (size_t)KS * 2 * 32 * sizeof(uint4)) +
+                        (size_t)8 * 32 * 8 * sizeof(float);
+    if (smem <= (size_t)kSmemBudget) {
+      void* fn = split == 2 ? (void*)lstm_bwd_mma_kernel<2> : (void*)lstm_bwd_mma_kernel<1>;
+      static size_t configured_mma[3] = {0, 0, 0};
+      if (smem > configured_mma[split]) {
+        RB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_mma[split] = smem;
+      }
+      uint4* db = reinterpret_cast<uint4*>(dgbuf);
+      void* args[] = {(void*)&dh_all, (void*)&whh, (void*)&lens, (void*)&gates_save, (void*)&c_save, (void*)&d,
+                      (void*)&dgates_all, (void*)&db, (void*)&counters};
+      RB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(2 * d.G), dim3(kLstmMmaBwdThreads), args, smem, st));
+      return after_launch();
     }
-    uint4* db = reinterpret_cast<uint4*>(dgbuf);
-    void* args[] = {(void*)&dh_all, (void*)&whh, (void*)&lens, (void*)&gates_save, (void*)&c_save, (void*)&d,
-                    (void*)&dgates_all, (void*)&db, (void*)&counters};
-    RB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_bwd_mma_kernel, dim3(2 * d.G), dim3(kLstmMmaBwdThreads), args, smem, st));
-    return after_launch();
+    RB_TRY(lstm_plan(H, &d));   // the split operands do not fit (H > ~400): fall through to the FMA kernel
   }
   if (H % 2) return RADTTS_ERR_UNSUPPORTED;
   const size_t smem = ((size_t)4 * H * 8 + (size_t)2 * (H / 2) * kLstmLd + (size_t)32 * 8 * kLstmMaxB) * sizeof(float);

@@ -64,12 +64,17 @@ class _BiLSTMFn(torch.autograd.Function):
         # under autocast (where cuDNN would run the LSTM in half precision) the recurrent product uses bf16 operands
         # on tensor cores; state, gates and outputs stay fp32.  The backward pass follows the forward's precision.
         low_prec = torch.is_autocast_enabled()
+        # recurrence precision: bf16 operands under autocast; in fp32, where cuDNN's RNN would be allowed TF32
+        # (torch.backends.cudnn.allow_tf32, the default), split-bf16 operands (16 mantissa bits) on tensor cores;
+        # the exact fp32 FMA kernel otherwise
+        prec = 1 if low_prec else (2 if torch.backends.cudnn.allow_tf32 else 0)
         _lib.check(L.radtts_lstm_forward(_lib.ptr(gx), _lib.ptr(whh), _lib.ptr(lens), T, B, H, _lib.ptr(h_all),
                                          _lib.ptr(gates), _lib.ptr(cs), _lib.ptr(ws), ctypes.c_size_t(nws),
-                                         1 if low_prec else 0, _lib.stream_of(x_tm)), "radtts_lstm_forward")
+                                         prec, _lib.stream_of(x_tm)), "radtts_lstm_forward")
         if need_bwd:
             ctx.save_for_backward(x_tm, lens, w_ih, whh, gates, cs, h_all)
             ctx.low_prec = low_prec
+            ctx.prec = prec
         return h_all
 
     @staticmethod
@@ -85,7 +90,7 @@ class _BiLSTMFn(torch.autograd.Function):
         ws = torch.empty(nws, dtype=torch.uint8, device=dev)
         _lib.check(L.radtts_lstm_backward(_lib.ptr(dh_all), _lib.ptr(whh), _lib.ptr(lens), _lib.ptr(gates), _lib.ptr(cs),
                                           T, B, H, _lib.ptr(dg), _lib.ptr(ws), ctypes.c_size_t(nws),
-                                          1 if ctx.low_prec else 0, _lib.stream_of(x_tm)), "radtts_lstm_backward")
+                                          ctx.prec, _lib.stream_of(x_tm)), "radtts_lstm_backward")
         mm = torch.bfloat16 if ctx.low_prec else torch.float32   # plain library GEMMs; bf16 under autocast
         dg2 = dg.reshape(2, T * B, 4 * H)
         dgm = dg2.to(mm)

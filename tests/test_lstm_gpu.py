@@ -97,3 +97,35 @@ def test_bilstm_bf16_tensor_core_path(cuda_lib, In, H, B, T):
     for n, p in lstm.named_parameters():
         err = float((p.grad - ref[n]).norm() / (ref[n].norm() + 1e-12))
         assert err < 5e-2, (n, err)
+
+
+@pytest.mark.parametrize("In,H,B,T", [(512, 256, 32, 37), (64, 40, 5, 23)])
+def test_bilstm_split_bf16_path_is_tf32_grade(cuda_lib, In, H, B, T):
+    """fp32 LSTMs with cuDNN's TF32 switch on (the PyTorch default) run the recurrence with hi + lo bf16 operands
+    (16 mantissa bits, fp32 accumulate) and the GEMMs around it in TF32, like cuDNN's own RNN under that switch.
+    Bar: within 1e-3 abs of the exact fp32 path on outputs (|h| < 1; measured 2e-4, dominated by the TF32 input
+    projection), 5e-3 relative (norm) on gradients."""
+    torch.manual_seed(0)
+    lstm = nn.LSTM(In, H, 1, batch_first=True, bidirectional=True).cuda()
+    x = (torch.randn(B, T, In, device="cuda") * 0.5).requires_grad_(True)
+    lens = torch.randint(max(1, T // 3), T + 1, (B,), device="cuda")
+    lens[0] = T
+    w = torch.randn(B, T, 2 * H, device="cuda")
+    res = {}
+    saved = torch.backends.cudnn.allow_tf32
+    try:
+        for flag in (False, True):
+            torch.backends.cudnn.allow_tf32 = flag
+            lstm.zero_grad()
+            x.grad = None
+            y = lstm_ops.bilstm(lstm, x, lens)
+            (y * w).sum().backward()
+            res[flag] = (y.detach().clone(), x.grad.clone(), {n: p.grad.clone() for n, p in lstm.named_parameters()})
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved
+    (y0, gx0, gp0), (y1, gx1, gp1) = res[False], res[True]
+    assert float((y1 - y0).abs().max()) < 1e-3, float((y1 - y0).abs().max())
+    # the input-projection / weight-gradient GEMMs around the recurrence are TF32 when the switch is on: 5e-3 there
+    assert float((gx1 - gx0).norm() / gx0.norm()) < 5e-3
+    for n in gp0:
+        assert float((gp1[n] - gp0[n]).norm() / (gp0[n].norm() + 1e-12)) < 5e-3, n
