@@ -122,20 +122,20 @@ class DenseLayer(nn.Module):
 
 
 class LengthRegulator(nn.Module):
-    """Token -> frame expansion (reference common.py:171-200), vectorised: one repeat_interleave per batch
-    instead of a Python loop over tokens."""
+    """Token -> frame expansion (reference common.py:171-200).  The reference loops over tokens in Python; here frame t
+    of utterance b takes token searchsorted(cumsum(dur[b]), t) -- one batched index computation and one gather, with a
+    single host read (the longest output, which fixes the result's shape)."""
 
     def forward(self, x, dur):
         # x (B, N, C), dur (B, N); expanded_len = int(dur + 0.5)
         reps = (dur.float() + 0.5).floor().long().clamp(min=0)
-        total = reps.sum(1)
+        ends = torch.cumsum(reps, 1)                                   # (B, N) exclusive end frame of every token
+        total = ends[:, -1]
         max_len = int(total.max())
-        out = x.new_zeros(x.shape[0], max_len, x.shape[2])
-        for b in range(x.shape[0]):
-            n = int(total[b])
-            if n:
-                out[b, :n] = torch.repeat_interleave(x[b], reps[b], dim=0)
-        return out
+        t = torch.arange(max_len, device=x.device)[None, :].expand(x.shape[0], -1).contiguous()
+        idx = torch.searchsorted(ends, t, right=True).clamp(max=x.shape[1] - 1)   # (B, max_len) token of every frame
+        out = torch.gather(x, 1, idx[:, :, None].expand(-1, -1, x.shape[2]))
+        return out * (t < total[:, None])[:, :, None].to(out.dtype)
 
 
 def _apply_lstm_norm(lstm, kind):
@@ -269,8 +269,13 @@ class Encoder(nn.Module):
         return out
 
     def infer(self, x):
+        """reference common.py:375-384: the whole (padded) batch goes through the LSTM unpacked, i.e. every utterance at
+        the full padded length -- the persistent recurrence kernel with lens = T for all."""
         with torch.autocast(device_type=x.device.type, enabled=False):
             x = self._convs(x.float()).transpose(1, 2)
+            if lstm_ops.supported(self.lstm, x):
+                full = torch.full((x.shape[0],), x.shape[1], dtype=torch.int32, device=x.device)
+                return lstm_ops.bilstm(self.lstm, x, full)
             self.lstm.flatten_parameters()
             return self.lstm(x)[0]
 
