@@ -12,15 +12,24 @@ from torch.nn import functional as F
 from .common import get_mask_from_lengths
 
 
-def compute_flow_loss(z, log_det_W_list, log_s_list, n_elements, n_dims, mask, sigma=1.0):
-    """(prior NLL - sum log_s - n_elements * sum log|det W|) / (n_elements * n_dims); does not mutate its inputs."""
+def compute_flow_loss(z, log_det_W_list, log_s_list, n_elements, n_dims, mask, sigma=1.0, packed=None):
+    """(prior NLL - sum log_s - n_elements * sum log|det W|) / (n_elements * n_dims); does not mutate its inputs.
+    packed = (z_packed, [log_s_packed, ...]): the same tensors in the packed-row layout of the decoder kernels, whose
+    padding rows are exactly zero -- plain sums, no mask (only valid when `mask` is the decoder's own frame mask)."""
     log_s_total = 0.0
-    for log_s in log_s_list:
-        log_s_total = log_s_total + torch.sum(log_s * mask)
+    if packed is not None:
+        for log_s in packed[1]:
+            log_s_total = log_s_total + torch.sum(log_s)
+    else:
+        for log_s in log_s_list:
+            log_s_total = log_s_total + torch.sum(log_s * mask)
     log_det_total = 0.0
     if len(log_det_W_list):
         log_det_total = torch.stack([ld.reshape(()) for ld in log_det_W_list]).sum() * n_elements
-    z = z * mask
+    if packed is not None:
+        z = packed[0]
+    else:
+        z = z * mask
     prior_nll = torch.sum(z * z) / (2 * sigma * sigma)
     denom = n_elements * n_dims
     return (prior_nll - log_s_total - log_det_total) / denom, prior_nll / denom
@@ -157,8 +166,14 @@ class RADTTSLoss(nn.Module):
             n_elements = out_lens.sum() // self.n_group_size
             z = model_output["z_mel"]
             mask = get_mask_from_lengths(out_lens // self.n_group_size, z.shape[2])[:, None].float()
-            loss_mel, loss_prior_mel = compute_flow_loss(z, model_output["log_det_W_list"], model_output["log_s_list"],
-                                                         n_elements, z.size(1), mask, self.sigma)
+            packed = None
+            rb = getattr(z, "_rb_packed", None)
+            ls_list = model_output["log_s_list"]
+            if rb is not None and rb[3] is out_lens and len(rb[2]) == len(ls_list) and \
+                    all(a is b for a, b in zip(rb[2], ls_list)):
+                packed = (rb[0], rb[1])    # produced by ops.decoder_forward for exactly these tensors and lengths
+            loss_mel, loss_prior_mel = compute_flow_loss(z, model_output["log_det_W_list"], ls_list,
+                                                         n_elements, z.size(1), mask, self.sigma, packed=packed)
             loss_dict["loss_mel"] = (loss_mel, 1.0)
             loss_dict["loss_prior_mel"] = (loss_prior_mel, 0.0)
         ctc = self.attn_ctc_loss(model_output["attn_logprob"], in_lens, out_lens)

@@ -508,7 +508,12 @@ def decoder_forward(model, mel, context, out_lens):
     actives = _active_channels(model, z_ld)
     z, log_det_list, log_s = flow_stack_packed(list(model.flows), z, ctxp, plan, z_ld, actives, False, prec)
     log_s_list = [unpack(ls, plan, c // 2, 1, 0) for ls, c in zip(log_s, actives)]
-    return unpack(z, plan, z_ld, 1, 0), log_det_list, log_s_list
+    z_mel = unpack(z, plan, z_ld, 1, 0)
+    # the packed originals ride along (rows of gaps / beyond the lengths are exactly zero in all of them), so that the
+    # flow loss can sum them directly instead of masking and reducing the padded (B, C, T') copies -- and its gradient
+    # then enters the flow stack's backward without the unpack / pack round trip (loss.RADTTSLoss)
+    z_mel._rb_packed = (z, list(log_s), list(log_s_list), out_lens)
+    return z_mel, log_det_list, log_s_list
 
 
 def decoder_inverse(model, residual, context, out_lens):
