@@ -195,6 +195,47 @@ __global__ void __launch_bounds__(256) prep_convs_kernel(const PrepConvParams p)
   constexpr int k = K;
   const int N = p.N, C = p.C;
   const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+  // Whole tiles with 16-byte aligned rows (always the case for the WN convs: N, C multiples of 64) move as 16-byte
+  // vectors: float4 loads, 8 x bf16 / 4 x fp32 stores.  Anything else takes the element-wise path.
+  const bool vec = (n0 + 32 <= N) && (c0 + 64 <= C) && (C % 8 == 0) && (N % 8 == 0) && ((it.lddT | it.dcolT) % 8 == 0);
+  if (vec) {
+    constexpr int kQ = 16 * K;            // float4 per weight row of this tile (64 channels x K taps, contiguous)
+    for (int idx = threadIdx.x; idx < 32 * kQ; idx += 256) {
+      const int n = idx / kQ, q = idx - n * kQ;
+      const float sc = it.scale[n0 + n];
+      const float4 v4 = *reinterpret_cast<const float4*>(it.v + ((size_t)(n0 + n) * C + c0) * K + 4 * q);
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = 4 * q + j, c = r / K, t = r - c * K;
+        tile[t * kPlane + n * 65 + c] = vv[j] * sc;
+      }
+    }
+    __syncthreads();
+    T* dst = reinterpret_cast<T*>(it.dst);
+    const size_t ldw = (size_t)K * C;
+    constexpr int kPer = 16 / sizeof(T);  // elements per 16-byte store
+    // forward layout: (t, n) rows of 64 consecutive channels
+    for (int idx = threadIdx.x; idx < K * 32 * (64 / kPer); idx += 256) {
+      const int cc = idx % (64 / kPer), n = (idx / (64 / kPer)) & 31, t = idx / (32 * (64 / kPer));
+      float vals[kPer];
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) vals[j] = tile[t * kPlane + n * 65 + cc * kPer + j];
+      Act<T>::template stv<kPer>(dst + (size_t)(n0 + n) * ldw + (size_t)t * C + c0 + cc * kPer, vals);
+    }
+    if (it.dstT) {
+      // transposed layout: (t, c) rows of 32 consecutive output channels
+      T* dstT = reinterpret_cast<T*>(it.dstT);
+      for (int idx = threadIdx.x; idx < K * 64 * (32 / kPer); idx += 256) {
+        const int nn = idx % (32 / kPer), c = (idx / (32 / kPer)) & 63, t = idx / (64 * (32 / kPer));
+        float vals[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) vals[j] = tile[t * kPlane + (nn * kPer + j) * 65 + c];
+        Act<T>::template stv<kPer>(dstT + (size_t)(c0 + c) * it.lddT + it.dcolT + (size_t)t * N + n0 + nn * kPer, vals);
+      }
+    }
+    return;
+  }
   const int per_row = 64 * k;
   for (int idx = threadIdx.x; idx < 32 * per_row; idx += 256) {
     const int n = idx / per_row, r = idx - n * per_row;
