@@ -4,12 +4,13 @@
 // alignment.py:31-59).  One CTA per utterance:
 //   producer warp : streams the utterance's (out_len x T2) cost rows HBM -> smem ring with 1-D bulk async copies
 //                   (cp.async.bulk + mbarrier), many KB in flight per SM;
-//   W DP warps    : warp w owns text columns [32w, 32w+32), one column per lane, its running score in a register.
-//                   Row i needs only row i-1 (columns j-1, j): inside a warp that is one __shfl_up; across warps the
-//                   last lane's score goes through a small smem ring and warp w simply trails warp w-1 by a few rows
-//                   (skewed wavefront, no CTA-wide barrier in the loop).  The diagonal/straight decision of every
-//                   cell is ONE BIT: a warp ballot per row yields the 32 decisions of the warp's columns as one word,
-//                   already in natural column order;
+//   W DP warps    : warp w owns 32 NC text columns, NC (= 2 for T2 > 32) per lane (lane l: columns l, l + 32 of the
+//                   block), running scores in registers.  Row i needs only row i-1 (columns j-1, j): inside a warp one
+//                   rotate-by-one shuffle per column set; across warps the last column's score goes through a smem ring
+//                   in which the VALUE IS ITS OWN FLAG (signalling-NaN sentinel, see dp_warp), checked once per group of
+//                   four rows, so warp w trails warp w-1 by a few rows (skewed wavefront, no CTA-wide barrier, no
+//                   fences in the loop).  The diagonal/straight decision of every cell is ONE BIT: a warp ballot per
+//                   row yields the 32 decisions of a column set as one word, already in natural column order;
 //   fill warps    : zero the utterance's slab of the dense hard map while the DP runs;
 //   then warp 0 backtracks 32 rows at a time with the bit windows held in registers (no dependent smem latency per
 //   step), and all threads scatter the ones, frame->token indices and durations.
