@@ -324,29 +324,6 @@ struct EpiCoupling {
 // ------------------------------------------------------------------------------------------------------
 // backward epilogues
 // ------------------------------------------------------------------------------------------------------
-// dgrad of `end`: acc = dL/d(sum_i r_i); emits g_u_i = acc * softplus'(r_i) for every layer i.
-template <typename T>
-struct EpiEndDgrad {
-  const T* r;  int ldr;   // [rows][n_layers * n_ch]
-  T* gu;                  // [n_layers][rows_alloc][n_ch]
-  int n_layers, n_ch, rows_alloc;
-  RowMeta meta;
-  __device__ __forceinline__ RowState prep(int row) const { return RowState{meta.valid(row), 1.f}; }
-  __device__ __forceinline__ const float* colvec() const { return nullptr; }
-  template <int W>
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
-                                             const float (&)[W]) const {
-    const bool ok = rs.ok;
-    for (int l = 0; l < n_layers; ++l) {
-      float rv[W], y[W];
-      Act<T>::template ldv<W>(r + (size_t)row * ldr + l * n_ch + col0, rv);
-#pragma unroll
-      for (int i = 0; i < W; ++i) y[i] = ok ? acc[i] * softplus_grad_t<T>(rv[i]) : 0.f;
-      Act<T>::template stv<W>(gu + ((size_t)l * rows_alloc + row) * n_ch + col0, y);
-    }
-  }
-};
-
 // dgrad through a softplus'ed (partial) conv output x:  g_v = acc * softplus'(x) * ratio   (valid rows)
 // with act == ACT_NONE / partial == 0 it is a plain masked store (g_x0 of `start`).
 template <typename T, int ACT = -1>

@@ -198,13 +198,6 @@ def unpack(packed, plan, C, g=1, col_off=0):
 # ------------------------------------------------------------------------------------------------------
 # flow step
 # ------------------------------------------------------------------------------------------------------
-def _effective(conv):
-    """Weight of a (possibly weight-normed) conv: w = g * v / ||v|| (torch.nn.utils.weight_norm, dim 0)."""
-    if hasattr(conv, "weight_v"):
-        return torch._weight_norm(conv.weight_v, conv.weight_g, 0)
-    return conv.weight
-
-
 def _flow_dims(flow, z_ld, c_active):
     wn = flow.affine_tfn.affine_param_predictor
     scaling = flow.affine_tfn.scaling_fn
