@@ -1,0 +1,64 @@
+"""CPU checks of host-side pieces that are plain tensor programs (no CUDA library involved): the vectorised
+LengthRegulator against the reference's per-token loop semantics (common.py:171-200), and the differentiable spline /
+coupling formulation used for the attribute flows' training direction against the oracle restatement of
+splines.py:221-319."""
+import math
+
+import pytest
+import torch
+
+from oracle import flow as oflow
+from radtts_b200 import ops
+from radtts_b200.common import LengthRegulator
+
+
+def test_length_regulator_matches_token_loop():
+    torch.manual_seed(0)
+    x = torch.randn(4, 9, 6)
+    dur = torch.tensor([[2, 0, 3, 1, 0, 0, 4, 1, 1], [1] * 9, [0, 0, 5, 0, 2, 0, 0, 0, 0], [0] * 9]).float()
+    dur[0, 0] = 1.6                                    # rounds to 2 (int(dur + 0.5))
+    out = LengthRegulator()(x, dur)
+    reps = (dur + 0.5).floor().long()
+    ref = torch.zeros(4, int(reps.sum(1).max()), 6)
+    for b in range(4):
+        rows = [x[b, j] for j in range(9) for _ in range(int(reps[b, j]))]   # the reference's loop over tokens
+        if rows:
+            ref[b, :len(rows)] = torch.stack(rows)
+    assert out.shape == ref.shape and torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_spline_autograd_formulation_matches_oracle(inverse):
+    torch.manual_seed(1)
+    n, h, k = 257, 3, 16
+    x = torch.rand(n, h) * 1.6 - 0.3                    # some elements outside [0, 1): identity there
+    w = torch.randn(n, h, k)
+    v = torch.randn(n, h, k + 1)
+    want, want_lj = oflow.rq_spline_unbounded(x.clone(), w, v, inverse)
+    xg = x.clone().requires_grad_(True)
+    wg, vg = w.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    got, got_lj = ops._rq_spline_autograd(xg, wg, vg, inverse)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+    if not inverse:
+        assert torch.allclose(got_lj, want_lj, rtol=1e-5, atol=1e-6)
+        (got.sum() + got_lj.sum()).backward()
+    else:
+        got.sum().backward()
+    for t in (xg.grad, wg.grad, vg.grad):
+        assert t is not None and bool(torch.isfinite(t).all())
+    outside = (x < 0) | (x >= 1)
+    assert torch.equal(xg.grad[outside], torch.ones_like(xg.grad[outside]))   # identity outside the unit interval
+    assert float(wg.grad[outside].abs().max()) == 0.0
+
+
+def test_scale_and_log_modes():
+    x = torch.linspace(-3, 3, 13)
+    s, ls = ops._scale_and_log(x, "tanh")
+    assert torch.allclose(s, torch.tanh(x) + 1 + 1e-6) and torch.allclose(ls, torch.log(s))
+    s, ls = ops._scale_and_log(x, "exp")
+    assert torch.allclose(s, torch.exp(x)) and torch.equal(ls, x)
+    s, ls = ops._scale_and_log(x, "sigmoid")
+    assert torch.allclose(s, torch.sigmoid(x + 10) + 1e-6)
+    s, ls = ops._scale_and_log(x, "translate")
+    assert float(s.min()) == 1.0 and float(ls.abs().max()) == 0.0
+    assert math.isfinite(float(ls.sum()))
