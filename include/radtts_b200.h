@@ -63,10 +63,11 @@ RADTTS_API int radtts_mas_forward(const float* attn, int is_prob, const int64_t*
                        size_t ws_bytes, void* stream);
 
 
-/* Diagnostic: globaltimer (ns) phase marks of CTA 0 of the last radtts_mas_forward launch, copied to 8 host
- * words: [0] start, [1] first DP warp done, [2] DP + fill done, [3] backtrack done, [4] end, [5] fill done.
- * Synchronises the device. */
-RADTTS_API int radtts_mas_debug_timeline(unsigned long long* out8_host);
+/* Diagnostic: phase marks of CTA 0 of the last radtts_mas_forward launch, copied to SIXTEEN host words:
+ * globaltimer (ns): [0] start, [1] first DP warp done, [2] DP + fill done, [3] backtrack done, [4] end, [5] fill done;
+ * clock64: [6] start, [7] first DP warp done; last DP warp, cycle sums over its chunks: [8] waiting for data, [9] row
+ * loop, [11] chunks, [12] rows per chunk, [13] row-loop cycles of warp 0, [14] hand-off spins.  Synchronises the device. */
+RADTTS_API int radtts_mas_debug_timeline(unsigned long long* out16_host);
 
 /* ------------------------------------------------------------------------------------------------
  * Packed frame layout ("frame plan").

@@ -569,9 +569,9 @@ extern "C" int radtts_mas_forward(const float* attn, int is_prob, const int64_t*
   return after_launch();
 }
 
-extern "C" int radtts_mas_debug_timeline(unsigned long long* out8_host) {
-  if (!out8_host) return RADTTS_ERR_INVALID_ARG;
+extern "C" int radtts_mas_debug_timeline(unsigned long long* out16_host) {
+  if (!out16_host) return RADTTS_ERR_INVALID_ARG;
   RB_CUDA(cudaDeviceSynchronize());
-  RB_CUDA(cudaMemcpyFromSymbol(out8_host, g_mas_timeline, 16 * sizeof(unsigned long long)));
+  RB_CUDA(cudaMemcpyFromSymbol(out16_host, g_mas_timeline, 16 * sizeof(unsigned long long)));
   return 0;
 }
