@@ -257,6 +257,13 @@ RADTTS_API int radtts_conv_rows(const void* prepared, int c_out, int c_in_pad, i
 RADTTS_API int radtts_rqspline_apply(const float* x, const float* params, int B, int C, int T, int n_bins, int inverse,
                                      float left, float right, float bottom, float top, float* y, float* log_s,
                                      void* stream);
+/* Backward of radtts_rqspline_apply in the forward direction (training the attribute flows): g_y (B, C, T) and g_log_s
+ * (B, 1, T) may be NULL (zeros); g_x (B, C, T) = gradient w.r.t. the coupling input (pass-through half = g_y), g_params
+ * (B, (C/2)(2 n_bins + 1), T) = gradient w.r.t. the raw spline parameters.  Closed form of what autograd derives for
+ * splines.py:254-319 (blueprint: oracle/spline_grad.py). */
+RADTTS_API int radtts_rqspline_backward(const float* x, const float* params, const float* g_y, const float* g_log_s, int B,
+                                        int C, int T, int n_bins, float left, float right, float bottom, float top,
+                                        float* g_x, float* g_params, void* stream);
 /* Affine coupling apply (reference common.py:782-784,821-832): params (B, C, T) = [raw scale | translation];
  * scaling 0 tanh, 1 exp, 2 sigmoid, 3 translate.  log_s (B, C/2, T) forward only, may be NULL. */
 RADTTS_API int radtts_affine_apply(const float* z, const float* params, int B, int C, int T, int scaling, int inverse,

@@ -81,6 +81,97 @@ __global__ void __launch_bounds__(128) rqspline_kernel(const float* __restrict__
   if (log_s && !inverse) log_s[(size_t)b * T + t] = ls_total + (float)h * (logf(top - bottom) - logf(right - left));
 }
 
+// Backward of the forward-direction spline coupling (training the attribute flows): closed-form gradients, term by term
+// as in oracle/spline_grad.py (which is pinned against autograd).  One thread per (b, t); for every transformed channel
+// the forward quantities are recomputed from the 2 nb + 1 raw parameters, then
+//   g_x (B, C, T): pass-through half = g_y, transformed half = d y / d x (+ d log_s / d x)
+//   g_params (B, h (2 nb + 1), T): gradients of the raw widths / heights (zero where x is outside the spline's interval)
+__global__ void __launch_bounds__(128) rqspline_bwd_kernel(const float* __restrict__ x, const float* __restrict__ params,
+                                                           const float* __restrict__ g_y, const float* __restrict__ g_log_s,
+                                                           int B, int C, int h, int T, int nb, float left, float right,
+                                                           float bottom, float top, float* __restrict__ g_x,
+                                                           float* __restrict__ g_params) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= T) return;
+  const float eps = 1.1920929e-07f;
+  const int np = 2 * nb + 1;
+  const float gl = g_log_s ? g_log_s[(size_t)b * T + t] : 0.f;     // d L / d log_j, the same for every channel
+  for (int c = 0; c < h; ++c) {
+    const size_t i0 = ((size_t)b * C + c) * T + t;
+    g_x[i0] = g_y ? g_y[i0] : 0.f;
+  }
+  for (int c = 0; c < h; ++c) {
+    const size_t xi = ((size_t)b * C + h + c) * T + t;
+    const float xn = (x[xi] - left) / (right - left);
+    const float g_out = (g_y ? g_y[xi] : 0.f) * (top - bottom);    // y = out_n (top - bottom) + bottom
+    float* gp = g_params + ((size_t)b * h * np + (size_t)c * np) * T + t;
+    if (!(xn >= 0.f && xn < 1.f)) {                                // identity outside the interval
+      g_x[xi] = g_out / (right - left);
+      for (int i = 0; i < np; ++i) gp[(size_t)i * T] = 0.f;
+      continue;
+    }
+    const float* p = params + ((size_t)b * h * np + (size_t)c * np) * T + t;
+    float w[kMaxSplineBins], v[kMaxSplineBins + 1], e[kMaxSplineBins + 1], gw[kMaxSplineBins], gv[kMaxSplineBins + 1];
+    float m = -CUDART_INF_F;
+    for (int i = 0; i < nb; ++i) { w[i] = p[(size_t)i * T]; m = fmaxf(m, w[i]); }
+    float s = 0.f;
+    for (int i = 0; i < nb; ++i) { w[i] = expf(w[i] - m); s += w[i]; }
+    for (int i = 0; i < nb; ++i) w[i] /= s;
+    float vm = -CUDART_INF_F;
+    int am = 0;
+    for (int i = 0; i <= nb; ++i) { v[i] = p[(size_t)(nb + i) * T]; if (v[i] > vm) { vm = v[i]; am = i; } }
+    for (int i = 0; i <= nb; ++i) { e[i] = expf(v[i] - vm); v[i] = e[i] + 1e-8f; }
+    float S = 0.f;
+    for (int i = 0; i < nb; ++i) S += (v[i] + v[i + 1]) / 2.f * w[i];
+    for (int i = 0; i <= nb; ++i) v[i] /= S;
+    // bin of xn in wc = cumsum(w) (last knot forced to 1), searchsorted(left)
+    float wc = 0.f, cdf = 0.f, w_lo = 0.f, c_lo = 0.f;
+    int bin = nb - 1;
+    bool found = false;
+    for (int i = 0; i < nb; ++i) {
+      const float wc_prev = wc, cdf_prev = cdf;
+      wc += w[i];
+      cdf += (v[i + 1] + v[i]) / 2.f * w[i];
+      const float knot = (i == nb - 1) ? 1.f : wc;
+      if (!found && knot >= xn) { found = true; bin = i; w_lo = wc_prev; c_lo = cdf_prev; }
+      if (!found && i == nb - 1) { w_lo = wc_prev; c_lo = cdf_prev; }
+    }
+    const float w_b = w[bin], v_b = v[bin], v_n = v[bin + 1];
+    const float alpha = (xn - w_lo) / fmaxf(w_b, eps);
+    const float D = v_n - v_b, L = v_b + alpha * D;
+    const float cval = alpha * alpha / 2.f * D * w_b + alpha * v_b * w_b + c_lo;
+    const float gy = (cval > eps && cval < 1.f - eps) ? g_out : 0.f;         // the output clamp's gradient
+    const float g_alpha = gy * w_b * L + gl * D / L;
+    g_x[xi] = g_alpha / w_b / (right - left);
+    for (int i = 0; i < nb; ++i) gw[i] = 0.f;
+    for (int i = 0; i <= nb; ++i) gv[i] = 0.f;
+    gw[bin] += gy * (alpha * alpha / 2.f * D + alpha * v_b) - g_alpha * alpha / w_b;
+    gv[bin] += gy * (alpha - alpha * alpha / 2.f) * w_b + gl * (1.f - alpha) / L;
+    gv[bin + 1] += gy * alpha * alpha / 2.f * w_b + gl * alpha / L;
+    for (int j = 0; j < bin; ++j) {                                            // the prefix sums wc0_b and cdf0_b
+      gw[j] += -g_alpha / w_b + gy * (v[j] + v[j + 1]) / 2.f;
+      gv[j] += gy * w[j] / 2.f;
+      gv[j + 1] += gy * w[j] / 2.f;
+    }
+    float dot = 0.f;
+    for (int i = 0; i <= nb; ++i) dot += gv[i] * v[i];
+    for (int i = 0; i < nb; ++i) gw[i] -= dot * (v[i] + v[i + 1]) / 2.f;     // S depends on w
+    float gsum = 0.f;
+    for (int i = 0; i <= nb; ++i) {                                            // v = u / S, u = e + 1e-8
+      const float wl = i > 0 ? w[i - 1] : 0.f, wr = i < nb ? w[i] : 0.f;
+      const float gu = (gv[i] - dot * (wl + wr) / 2.f) / S;
+      gv[i] = gu * e[i];                                                       // d / d v~_i (before the max's share)
+      gsum += gv[i];
+    }
+    gv[am] -= gsum;                                                            // the max's sub-gradient, as autograd
+    float wdot = 0.f;
+    for (int i = 0; i < nb; ++i) wdot += gw[i] * w[i];
+    for (int i = 0; i < nb; ++i) gp[(size_t)i * T] = w[i] * (gw[i] - wdot);    // softmax
+    for (int i = 0; i <= nb; ++i) gp[(size_t)(nb + i) * T] = gv[i];
+  }
+}
+
 // Affine coupling apply: params (B, 2h, T) = [raw scale | translation]; z (B, 2h, T).
 __global__ void __launch_bounds__(256) affine_apply_kernel(const float* __restrict__ z, const float* __restrict__ params,
                                                            int h, int T, int scaling, int inverse, float* __restrict__ y,
@@ -147,5 +238,16 @@ extern "C" int radtts_pointwise_conv_small(const float* x, const float* w, int B
   if (C > 16) return RADTTS_ERR_UNSUPPORTED;
   dim3 grid(ceil_div(T, 256), B);
   pointwise_small_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, C, T, y);
+  return after_launch();
+}
+
+extern "C" int radtts_rqspline_backward(const float* x, const float* params, const float* g_y, const float* g_log_s, int B,
+                                        int C, int T, int n_bins, float left, float right, float bottom, float top,
+                                        float* g_x, float* g_params, void* stream) {
+  if (!x || !params || !g_x || !g_params || B <= 0 || C <= 0 || C % 2 || T <= 0 || n_bins <= 0) return RADTTS_ERR_INVALID_ARG;
+  if (n_bins > kMaxSplineBins) return RADTTS_ERR_UNSUPPORTED;
+  dim3 grid(ceil_div(T, 128), B);
+  rqspline_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, params, g_y, g_log_s, B, C, C / 2, T, n_bins, left, right,
+                                                             bottom, top, g_x, g_params);
   return after_launch();
 }

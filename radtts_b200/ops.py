@@ -595,11 +595,52 @@ def _rq_spline_autograd(x, w_tilde, v_tilde, inverse):
     return torch.where(inside, out, x), None
 
 
+class _SplineForwardFn(torch.autograd.Function):
+    """Forward-direction spline coupling apply (radtts_rqspline_apply) with the closed-form backward kernel
+    (radtts_rqspline_backward): z (B, C, T), params (B, h (2 nb + 1), T) -> (y, log_s)."""
+
+    @staticmethod
+    def forward(ctx, z, params, n_bins, left, right, bottom, top):
+        z = z.float().contiguous()
+        params = params.float().contiguous()
+        B, C, T = z.shape
+        y = torch.empty_like(z)
+        log_s = torch.empty((B, 1, T), dtype=torch.float32, device=z.device)
+        _lib.check(_lib.lib().radtts_rqspline_apply(_lib.ptr(z), _lib.ptr(params), B, C, T, n_bins, 0,
+                                                    ctypes.c_float(left), ctypes.c_float(right), ctypes.c_float(bottom),
+                                                    ctypes.c_float(top), _lib.ptr(y), _lib.ptr(log_s), _lib.stream_of(z)),
+                   "radtts_rqspline_apply")
+        ctx.save_for_backward(z, params)
+        ctx.consts = (n_bins, left, right, bottom, top)
+        return y, log_s
+
+    @staticmethod
+    def backward(ctx, g_y, g_log_s):
+        z, params = ctx.saved_tensors
+        n_bins, left, right, bottom, top = ctx.consts
+        B, C, T = z.shape
+        g_y = None if g_y is None else g_y.float().contiguous()
+        g_log_s = None if g_log_s is None else g_log_s.float().contiguous()
+        g_z = torch.empty_like(z)
+        g_p = torch.empty_like(params)
+        _lib.check(_lib.lib().radtts_rqspline_backward(_lib.ptr(z), _lib.ptr(params), _lib.ptr(g_y), _lib.ptr(g_log_s), B, C,
+                                                       T, n_bins, ctypes.c_float(left), ctypes.c_float(right),
+                                                       ctypes.c_float(bottom), ctypes.c_float(top), _lib.ptr(g_z),
+                                                       _lib.ptr(g_p), _lib.stream_of(z)), "radtts_rqspline_backward")
+        return g_z, g_p, None, None, None, None, None
+
+
 def _spline_coupling_autograd(layer, z, context, inverse, seq_lens):
     """SplineTransformationLayer.forward, use_quadratic=True (reference common.py:694-743)."""
     import math
     b, c, t = z.shape
     h = layer.half_mel_channels
+    if not inverse and z.is_cuda and not os.environ.get("RADTTS_SPLINE_AUTOGRAD"):
+        # parameter network on differentiable library ops, the spline itself on the fused kernels (forward + closed-form
+        # backward); z[:, :h] reaches the parameters through autograd, the Function returns the direct path
+        q = _simple_conv_net_autograd(layer.param_predictor, torch.cat((z[:, :h], context), 1), seq_lens)
+        return _SplineForwardFn.apply(z, q, layer.n_bins // 2, float(layer.left), float(layer.right),
+                                      float(layer.bottom), float(layer.top))
     z0, z1 = z[:, :h], z[:, h:]
     z1 = (z1 - layer.bottom) / (layer.top - layer.bottom) if inverse else (z1 - layer.left) / (layer.right - layer.left)
     nb = layer.n_bins

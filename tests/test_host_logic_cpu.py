@@ -62,3 +62,23 @@ def test_scale_and_log_modes():
     s, ls = ops._scale_and_log(x, "translate")
     assert float(s.min()) == 1.0 and float(ls.abs().max()) == 0.0
     assert math.isfinite(float(ls.sum()))
+
+
+def test_analytic_spline_backward_matches_autograd():
+    """oracle/spline_grad.py (closed-form gradients, the blueprint for a spline-backward kernel) vs autograd, float64."""
+    from oracle import spline_grad
+    torch.manual_seed(3)
+    n, k = 400, 16
+    x = (torch.rand(n, dtype=torch.float64) * 1.5 - 0.25)
+    w = torch.randn(n, k, dtype=torch.float64)
+    v = torch.randn(n, k + 1, dtype=torch.float64)
+    gy, gl = torch.randn(n, dtype=torch.float64), torch.randn(n, dtype=torch.float64)
+    xg, wg, vg = x.clone().requires_grad_(True), w.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    y, lj = ops._rq_spline_autograd(xg[:, None], wg[:, None, :], vg[:, None, :], False)
+    ((y[:, 0] * gy).sum() + (lj[:, 0] * gl).sum()).backward()
+    y2, lj2, g_x, g_w, g_v = spline_grad.rq_spline_forward_backward(x, w, v, gy, gl)
+    assert torch.allclose(y2, y[:, 0].detach(), rtol=1e-12, atol=1e-12)
+    assert torch.allclose(lj2, lj[:, 0].detach(), rtol=1e-12, atol=1e-12)
+    assert torch.allclose(g_x, xg.grad, rtol=1e-9, atol=1e-10), float((g_x - xg.grad).abs().max())
+    assert torch.allclose(g_w, wg.grad, rtol=1e-8, atol=1e-10), float((g_w - wg.grad).abs().max())
+    assert torch.allclose(g_v, vg.grad, rtol=1e-8, atol=1e-10), float((g_v - vg.grad).abs().max())
