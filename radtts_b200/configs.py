@@ -12,11 +12,14 @@ def _bottleneck(non_linearity="relu", **extra):
     return d
 
 
-def _dap(kernel_size=3, p_dropout=0.25, take_log_of_input=False, **arch_extra):
+def _dap(kernel_size=3, p_dropout=0.25, take_log_of_input=False, use_transformer=None, **arch_extra):
     arch = {"out_dim": 1, "n_layers": 2, "n_channels": 256, "kernel_size": kernel_size, "p_dropout": p_dropout}
     arch.update(arch_extra)
-    return {"name": "dap", "hparams": {"n_speaker_dim": 16, "bottleneck_hparams": _bottleneck(),
-                                       "take_log_of_input": take_log_of_input, "arch_hparams": arch}}
+    hp = {"n_speaker_dim": 16, "bottleneck_hparams": _bottleneck(), "take_log_of_input": take_log_of_input}
+    if use_transformer is not None:      # only config_ljs_dap.json spells the key out
+        hp["use_transformer"] = use_transformer
+    hp["arch_hparams"] = arch
+    return {"name": "dap", "hparams": hp}
 
 
 def _bgap(n_group_size):
@@ -52,7 +55,8 @@ _VARIANTS = {
     "bgap": dict(_ATTR, include_modules="decatndpmvpredapm", use_first_order_features=True,
                  f0_model_config=_bgap(2), energy_model_config=_bgap(4)),
     "dap": dict(_ATTR, include_modules="decatndpmvpredapm",
-                f0_model_config=_dap(kernel_size=11, p_dropout=0.5), energy_model_config=_dap()),
+                f0_model_config=_dap(kernel_size=11, p_dropout=0.5, use_transformer=False),
+                energy_model_config=_dap(use_transformer=False)),
 }
 
 LOSS_WEIGHTS = {"blank_logprob": -1, "ctc_loss_weight": 0.1, "binarization_loss_weight": 1.0, "dur_loss_weight": 1.0,

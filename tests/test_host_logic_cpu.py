@@ -82,3 +82,18 @@ def test_analytic_spline_backward_matches_autograd():
     assert torch.allclose(g_x, xg.grad, rtol=1e-9, atol=1e-10), float((g_x - xg.grad).abs().max())
     assert torch.allclose(g_w, wg.grad, rtol=1e-8, atol=1e-10), float((g_w - wg.grad).abs().max())
     assert torch.allclose(g_v, vg.grad, rtol=1e-8, atol=1e-10), float((g_v - vg.grad).abs().max())
+
+
+def test_model_configs_equal_the_reference_json_when_mounted():
+    """radtts_b200.configs mirrors configs/*.json: model_config of the reference (drop-in constructor keys)."""
+    import json
+    import os
+    from radtts_b200 import configs
+    ref_dir = os.path.join(os.environ.get("RADTTS_REFERENCE", "/root/reference"), "configs")
+    if not os.path.isdir(ref_dir):
+        pytest.skip("reference tree not mounted")
+    for name, fn in (("radtts", "config_ljs_radtts.json"), ("decoder", "config_ljs_decoder.json"),
+                     ("bgap", "config_ljs_bgap.json"), ("dap", "config_ljs_dap.json")):
+        with open(os.path.join(ref_dir, fn)) as f:
+            ref = json.load(f)["model_config"]
+        assert configs.model_config(name) == ref, name
