@@ -171,6 +171,40 @@ def gen_radtts_forward(ns):
           "loss_mel %.5f ctc %.5f bin %.5f" % (g["loss_mel"], g["loss_ctc"], g["loss_binarization"]))
 
 
+def gen_radtts_forward_soft(ns):
+    """config_ljs_radtts with binarize_attention=False (what the reference trains with before binarization_start_iter,
+    train.py:389-392): the context is bmm(text_enc, attn_soft^T), so the flow loss back-propagates into the attention
+    and the text encoder.  Full forward + RADTTSLoss + backward in eval mode (no dropout); gradients of EVERY parameter."""
+    import torch
+    from radtts_b200 import synth
+    model, cfg, sd = _ref_model(ns, "config_ljs_radtts.json")
+    B, T1, T2 = 2, 44, 15
+    batch = synth.synth_batch(B, T1, T2, seed=2468)
+    model.zero_grad()
+    out = model(batch["mel"], batch["speaker_ids"], batch["text"], batch["in_lens"], batch["out_lens"],
+                binarize_attention=False, attn_prior=batch["attn_prior"])
+    g = {"z_mel": out["z_mel"].detach().numpy(), "attn": out["attn"].detach().numpy(),
+         "log_det_W": np.array([float(x) for x in out["log_det_W_list"]], dtype=np.float32)}
+    crit = ns.loss.RADTTSLoss(sigma=1.0, n_group_size=2, loss_weights=cfg["train_config"]["loss_weights"])
+    ld = crit(out, batch["in_lens"], batch["out_lens"])
+    total = sum(v * w for v, w in ld.values() if w > 0)
+    total.backward()
+    g["loss_mel"] = np.float32(ld["loss_mel"][0].item())
+    g["loss_ctc"] = np.float32(ld["loss_ctc"][0].item())
+    g["total"] = np.float32(total.item())
+    names, sums, samples = [], [], []
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            sm, sp = _param_summary(p.grad)
+            names.append(k); sums.append(sm); samples.append(np.pad(sp, (0, 64 - len(sp))))
+    g["grad_names"] = np.array(names)
+    g["grad_sums"] = np.stack(sums)
+    g["grad_samples"] = np.stack(samples)
+    np.savez_compressed(os.path.join(GOLD, "radtts_forward_soft.npz"), **g)
+    print("wrote radtts_forward_soft.npz", os.path.getsize(os.path.join(GOLD, "radtts_forward_soft.npz")), "bytes;",
+          "total %.5f, %d parameter gradients" % (g["total"], len(names)))
+
+
 def gen_bgap(ns):
     """config_ljs_bgap: the two BGAP attribute flows (F0: group 2, energy: group 4), sampling (infer) and training
     (forward) directions, straight through the reference modules (attribute_prediction_model.py:187-224)."""
@@ -292,7 +326,7 @@ def gen_radtts_infer(ns):
           {k: v.shape for k, v in g.items() if k.endswith("mel")})
 
 
-GENERATORS = {"mas": gen_mas, "radtts_infer": gen_radtts_infer, "radtts_forward": gen_radtts_forward, "bgap": gen_bgap,
+GENERATORS = {"mas": gen_mas, "radtts_infer": gen_radtts_infer, "radtts_forward_soft": gen_radtts_forward_soft, "radtts_forward": gen_radtts_forward, "bgap": gen_bgap,
               "decoder_cfg_forward": gen_decoder_cfg_forward}
 
 if __name__ == "__main__":

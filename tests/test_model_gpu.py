@@ -176,3 +176,47 @@ def test_bgap_config_trains_end_to_end(cuda_lib):
         assert not missing, missing[:5]
         assert all(bool(torch.isfinite(g).all()) for _, g in got)
         assert sum(float(g.abs().sum()) for _, g in got) > 0
+
+
+def test_soft_attention_training_direction_matches_reference(golden_dir, cuda_lib):
+    """binarize_attention=False (the reference's regime before binarization_start_iter): context = bmm(text, attn_soft),
+    so the flow loss reaches the attention and the text encoder.  Forward values, loss and EVERY parameter gradient
+    against the reference's autograd (golden: oracle/make_golden.py::gen_radtts_forward_soft), fp32."""
+    g = np.load(os.path.join(golden_dir, "radtts_forward_soft.npz"))
+    torch.manual_seed(0)
+    m = RADTTS(**configs.model_config("radtts")).eval()
+    synth.load_synth(m, seed=1234)
+    m = m.cuda()
+    b = {k: v.cuda() for k, v in synth.synth_batch(2, 44, 15, seed=2468).items()}
+    crit = rloss.RADTTSLoss(sigma=1.0, n_group_size=2, loss_weights=configs.LOSS_WEIGHTS)
+    ops.set_precision("fp32")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out = m(b["mel"], b["speaker_ids"], b["text"], b["in_lens"], b["out_lens"], binarize_attention=False,
+                attn_prior=b["attn_prior"])
+        losses = crit(out, b["in_lens"], b["out_lens"])
+        total = sum(v * w for v, w in losses.values() if w > 0)
+        total.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        ops.set_precision(None)
+    lens = b["out_lens"] // 2
+    assert torch.allclose(out["attn"].detach().cpu(), torch.from_numpy(g["attn"]), rtol=1e-3, atol=1e-6)
+    assert torch.allclose(_valid(out["z_mel"].detach(), lens).cpu(), _valid(torch.from_numpy(g["z_mel"]), lens.cpu()),
+                          rtol=1e-3, atol=3e-4)
+    assert abs(float(losses["loss_mel"][0]) - float(g["loss_mel"])) < 1e-3 * abs(float(g["loss_mel"]))
+    assert abs(float(losses["loss_ctc"][0]) - float(g["loss_ctc"])) < 1e-3 * abs(float(g["loss_ctc"]))
+    assert abs(float(total) - float(g["total"])) < 1e-3 * abs(float(g["total"]))
+    params = dict(m.named_parameters())
+    bad = []
+    for name, summ in zip(g["grad_names"], g["grad_sums"]):
+        p = params[str(name)]
+        if p.grad is None:
+            bad.append((str(name), "no grad"))
+            continue
+        norm = float(p.grad.double().norm())
+        if abs(norm - summ[1]) > 5e-3 * summ[1] + 1e-7:
+            bad.append((str(name), norm, float(summ[1])))
+    assert not bad, bad[:8]
