@@ -205,6 +205,40 @@ def gen_radtts_forward_soft(ns):
           "total %.5f, %d parameter gradients" % (g["total"], len(names)))
 
 
+def gen_decoder_cfg_train(ns):
+    """config_ljs_decoder (decoder conditioned on F0 / energy / voicing, voicing predictor, unvoiced bias) in the usual
+    training regime (binarize_attention=True): RADTTSLoss incl. the vpred loss + binarization loss, backward, gradients
+    of every parameter.  eval mode (no dropout)."""
+    import torch
+    from radtts_b200 import synth
+    model, cfg, sd = _ref_model(ns, "config_ljs_decoder.json")
+    mc = cfg["model_config"]
+    B, T1, T2 = 2, 48, 16
+    batch = synth.synth_batch(B, T1, T2, seed=1357, with_attributes=True)
+    model.zero_grad()
+    out = model(batch["mel"], batch["speaker_ids"], batch["text"], batch["in_lens"], batch["out_lens"],
+                binarize_attention=True, attn_prior=batch["attn_prior"], f0=batch["f0"],
+                energy_avg=batch["energy_avg"], voiced_mask=batch["voiced_mask"], p_voiced=batch["p_voiced"])
+    lw = cfg["train_config"]["loss_weights"]
+    crit = ns.loss.RADTTSLoss(1.0, mc["n_group_size"], mc["dur_model_config"], mc["f0_model_config"],
+                              mc["energy_model_config"], mc["v_model_config"], lw)
+    ld = crit(out, batch["in_lens"], batch["out_lens"])
+    total = sum(v * w for v, w in ld.values() if w > 0)
+    total = total + ns.loss.AttentionBinarizationLoss()(out["attn"], out["attn_soft"]) * lw["binarization_loss_weight"]
+    total.backward()
+    g = {"attn": out["attn"].detach().numpy(), "total": np.float32(total.item()),
+         "loss_names": np.array(sorted(ld)), "loss_values": np.array([float(ld[k][0]) for k in sorted(ld)], dtype=np.float32)}
+    names, sums = [], []
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            names.append(k); sums.append(_param_summary(p.grad)[0])
+    g["grad_names"] = np.array(names)
+    g["grad_sums"] = np.stack(sums)
+    np.savez_compressed(os.path.join(GOLD, "decoder_cfg_train.npz"), **g)
+    print("wrote decoder_cfg_train.npz", os.path.getsize(os.path.join(GOLD, "decoder_cfg_train.npz")), "bytes;",
+          "total %.5f, losses %s, %d gradients" % (g["total"], dict(zip(g["loss_names"], g["loss_values"])), len(names)))
+
+
 def gen_bgap(ns):
     """config_ljs_bgap: the two BGAP attribute flows (F0: group 2, energy: group 4), sampling (infer) and training
     (forward) directions, straight through the reference modules (attribute_prediction_model.py:187-224)."""
@@ -326,7 +360,7 @@ def gen_radtts_infer(ns):
           {k: v.shape for k, v in g.items() if k.endswith("mel")})
 
 
-GENERATORS = {"mas": gen_mas, "radtts_infer": gen_radtts_infer, "radtts_forward_soft": gen_radtts_forward_soft, "radtts_forward": gen_radtts_forward, "bgap": gen_bgap,
+GENERATORS = {"mas": gen_mas, "radtts_infer": gen_radtts_infer, "radtts_forward_soft": gen_radtts_forward_soft, "decoder_cfg_train": gen_decoder_cfg_train, "radtts_forward": gen_radtts_forward, "bgap": gen_bgap,
               "decoder_cfg_forward": gen_decoder_cfg_forward}
 
 if __name__ == "__main__":

@@ -220,3 +220,49 @@ def test_soft_attention_training_direction_matches_reference(golden_dir, cuda_li
         if abs(norm - summ[1]) > 5e-3 * summ[1] + 1e-7:
             bad.append((str(name), norm, float(summ[1])))
     assert not bad, bad[:8]
+
+
+def test_decoder_config_training_gradients_match_reference(golden_dir, cuda_lib):
+    """config_ljs_decoder (F0 / energy / voicing conditioned decoder) in the binarized training regime: loss terms and
+    every parameter gradient against the reference's autograd (golden: gen_decoder_cfg_train), fp32."""
+    g = np.load(os.path.join(golden_dir, "decoder_cfg_train.npz"))
+    torch.manual_seed(0)
+    cfg = configs.model_config("decoder")
+    m = RADTTS(**cfg).eval()
+    synth.load_synth(m, seed=1234)
+    m = m.cuda()
+    b = {k: v.cuda() for k, v in synth.synth_batch(2, 48, 16, seed=1357, with_attributes=True).items()}
+    crit = rloss.RADTTSLoss(1.0, cfg["n_group_size"], cfg["dur_model_config"], cfg["f0_model_config"],
+                            cfg["energy_model_config"], cfg["v_model_config"], configs.LOSS_WEIGHTS)
+    ops.set_precision("fp32")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out = m(b["mel"], b["speaker_ids"], b["text"], b["in_lens"], b["out_lens"], binarize_attention=True,
+                attn_prior=b["attn_prior"], f0=b["f0"], energy_avg=b["energy_avg"], voiced_mask=b["voiced_mask"],
+                p_voiced=b["p_voiced"])
+        losses = crit(out, b["in_lens"], b["out_lens"])
+        total = sum(v * w for v, w in losses.values() if w > 0)
+        total = total + rloss.AttentionBinarizationLoss()(out["attn"], out["attn_soft"]) * \
+            configs.LOSS_WEIGHTS["binarization_loss_weight"]
+        total.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        ops.set_precision(None)
+    assert np.array_equal(out["attn"].detach().cpu().numpy(), g["attn"])
+    for name, want in zip(g["loss_names"], g["loss_values"]):
+        got = float(losses[str(name)][0])
+        assert abs(got - float(want)) < 1e-3 * abs(float(want)) + 1e-6, (str(name), got, float(want))
+    assert abs(float(total) - float(g["total"])) < 1e-3 * abs(float(g["total"]))
+    params = dict(m.named_parameters())
+    bad = []
+    for name, summ in zip(g["grad_names"], g["grad_sums"]):
+        p = params[str(name)]
+        if p.grad is None:
+            bad.append((str(name), "no grad"))
+            continue
+        norm = float(p.grad.double().norm())
+        if abs(norm - summ[1]) > 5e-3 * summ[1] + 1e-7:
+            bad.append((str(name), norm, float(summ[1])))
+    assert not bad, bad[:8]
