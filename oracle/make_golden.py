@@ -239,6 +239,37 @@ def gen_decoder_cfg_train(ns):
           "total %.5f, losses %s, %d gradients" % (g["total"], dict(zip(g["loss_names"], g["loss_values"])), len(names)))
 
 
+def gen_radtts_train(ns):
+    """config_ljs_radtts in the regime bench.py times (binarize_attention=True, flow + CTC + binarization losses): the
+    reference's full forward + RADTTSLoss + backward in eval mode; loss terms and gradients of every parameter."""
+    import torch
+    from radtts_b200 import synth
+    model, cfg, sd = _ref_model(ns, "config_ljs_radtts.json")
+    B, T1, T2 = 3, 52, 17
+    batch = synth.synth_batch(B, T1, T2, seed=97531)
+    model.zero_grad()
+    out = model(batch["mel"], batch["speaker_ids"], batch["text"], batch["in_lens"], batch["out_lens"],
+                binarize_attention=True, attn_prior=batch["attn_prior"])
+    lw = cfg["train_config"]["loss_weights"]
+    crit = ns.loss.RADTTSLoss(sigma=1.0, n_group_size=2, loss_weights=lw)
+    ld = crit(out, batch["in_lens"], batch["out_lens"])
+    total = sum(v * w for v, w in ld.values() if w > 0)
+    bin_loss = ns.loss.AttentionBinarizationLoss()(out["attn"], out["attn_soft"])
+    total = total + bin_loss * lw["binarization_loss_weight"]
+    total.backward()
+    g = {"attn": out["attn"].detach().numpy(), "total": np.float32(total.item()), "loss_bin": np.float32(bin_loss.item()),
+         "loss_mel": np.float32(ld["loss_mel"][0].item()), "loss_ctc": np.float32(ld["loss_ctc"][0].item())}
+    names, sums = [], []
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            names.append(k); sums.append(_param_summary(p.grad)[0])
+    g["grad_names"] = np.array(names)
+    g["grad_sums"] = np.stack(sums)
+    np.savez_compressed(os.path.join(GOLD, "radtts_train.npz"), **g)
+    print("wrote radtts_train.npz", os.path.getsize(os.path.join(GOLD, "radtts_train.npz")), "bytes; total %.5f, %d gradients"
+          % (g["total"], len(names)))
+
+
 def gen_bgap(ns):
     """config_ljs_bgap: the two BGAP attribute flows (F0: group 2, energy: group 4), sampling (infer) and training
     (forward) directions, straight through the reference modules (attribute_prediction_model.py:187-224)."""
@@ -360,7 +391,7 @@ def gen_radtts_infer(ns):
           {k: v.shape for k, v in g.items() if k.endswith("mel")})
 
 
-GENERATORS = {"mas": gen_mas, "radtts_infer": gen_radtts_infer, "radtts_forward_soft": gen_radtts_forward_soft, "decoder_cfg_train": gen_decoder_cfg_train, "radtts_forward": gen_radtts_forward, "bgap": gen_bgap,
+GENERATORS = {"mas": gen_mas, "radtts_infer": gen_radtts_infer, "radtts_forward_soft": gen_radtts_forward_soft, "decoder_cfg_train": gen_decoder_cfg_train, "radtts_train": gen_radtts_train, "radtts_forward": gen_radtts_forward, "bgap": gen_bgap,
               "decoder_cfg_forward": gen_decoder_cfg_forward}
 
 if __name__ == "__main__":

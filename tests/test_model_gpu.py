@@ -266,3 +266,44 @@ def test_decoder_config_training_gradients_match_reference(golden_dir, cuda_lib)
         if abs(norm - summ[1]) > 5e-3 * summ[1] + 1e-7:
             bad.append((str(name), norm, float(summ[1])))
     assert not bad, bad[:8]
+
+
+def test_benchmarked_training_regime_gradients_match_reference(model, golden_dir):
+    """config_ljs_radtts exactly as bench.py steps it (binarize_attention=True; flow + CTC + binarization losses), in
+    fp32: hard map bit-identical, loss terms and all parameter gradients against the reference's autograd (golden:
+    gen_radtts_train).  Covers the fused CTC gradient, the context gather's segment-sum backward, the packed flow loss."""
+    g = np.load(os.path.join(golden_dir, "radtts_train.npz"))
+    b = {k: v.cuda() for k, v in synth.synth_batch(3, 52, 17, seed=97531).items()}
+    crit = rloss.RADTTSLoss(sigma=1.0, n_group_size=2, loss_weights=configs.LOSS_WEIGHTS)
+    model.zero_grad()
+    ops.set_precision("fp32")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out = model(b["mel"], b["speaker_ids"], b["text"], b["in_lens"], b["out_lens"], binarize_attention=True,
+                    attn_prior=b["attn_prior"])
+        losses = crit(out, b["in_lens"], b["out_lens"])
+        total = sum(v * w for v, w in losses.values() if w > 0)
+        bin_loss = rloss.AttentionBinarizationLoss()(out["attn"], out["attn_soft"])
+        total = total + bin_loss * configs.LOSS_WEIGHTS["binarization_loss_weight"]
+        total.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        ops.set_precision(None)
+    assert np.array_equal(out["attn"].detach().cpu().numpy(), g["attn"])
+    for key, got in (("loss_mel", losses["loss_mel"][0]), ("loss_ctc", losses["loss_ctc"][0]), ("loss_bin", bin_loss),
+                     ("total", total)):
+        assert abs(float(got) - float(g[key])) < 1e-3 * abs(float(g[key])), (key, float(got), float(g[key]))
+    params = dict(model.named_parameters())
+    bad = []
+    for name, summ in zip(g["grad_names"], g["grad_sums"]):
+        p = params[str(name)]
+        if p.grad is None:
+            bad.append((str(name), "no grad"))
+            continue
+        norm = float(p.grad.double().norm())
+        if abs(norm - summ[1]) > 5e-3 * summ[1] + 1e-7:
+            bad.append((str(name), norm, float(summ[1])))
+    model.zero_grad()
+    assert not bad, bad[:8]
