@@ -99,6 +99,8 @@ class TrainStep:
         gradient all-reduce launched eagerly between them (collectives inside a capture hung in testing)."""
         assert self.capturable and self.fused_optimizer, "CUDA graphs need TrainStep(capturable=True, fused_optimizer=True)"
         from . import _lib
+        import gc
+        gc.collect()   # drop autograd graphs of earlier eager steps: their nodes remember the stream they were built on
         self.static_batch = {k: v.clone() for k, v in example_batch.items()}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
