@@ -1,6 +1,6 @@
 """TrainStep (radtts_b200/trainer.py): the flat-gradient-buffer / direct-accumulation / CTC-prefetch machinery must
 compute the same gradients as the plain autograd path it replaces.  (The captured-graph step itself is exercised by
-bench.py and smoke(); capturing AFTER an eager step on the legacy default stream is a known limitation)"""
+bench.py; capturing AFTER an eager step on the legacy default stream is a known limitation)"""
 import pytest
 import torch
 
