@@ -1,13 +1,13 @@
 // bf16 tcgen05 engine of the row GEMM (see rowgemm.cuh for the contraction it computes).
 //
-// Persistent, warp-specialised, one CTA per SM:
-//   warp 0      TMA producer: per k-block one 128x64 activation box (row-shifted per segment -- the dilated conv
+// Persistent, warp-specialised, one CTA per SM (roles on the warps the kernel body assigns: see the note there):
+//   warps 0-3   epilogue: tcgen05.ld of the fp32 accumulator (lane == output row), fused epilogue functor
+//               (bias / partial-conv renormalisation / softplus / affine coupling / ...), direct global stores
+//   warp 4      TMA producer: per k-block one 128x64 activation box (row-shifted per segment -- the dilated conv
 //               taps are nothing but different row coordinates of the same tensor map; out-of-range rows are
 //               zero-filled by the TMA unit) and one BNx64 weight box, 128B-swizzled, into a 4-stage smem ring
-//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16) x4 per k-block,
+//   warp 5      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16) x4 per k-block,
 //               accumulating in TMEM; tcgen05.commit releases smem stages and publishes finished accumulators
-//   warps 2-5   epilogue: tcgen05.ld of the fp32 accumulator (lane == output row), fused epilogue functor
-//               (bias / partial-conv renormalisation / softplus / affine coupling / ...), direct global stores
 // Two 256-column TMEM accumulators (all 512 columns) double-buffer the epilogue against the next tile's MMAs.
 #pragma once
 #include <cuda.h>
