@@ -376,6 +376,9 @@ class _FlowStackFn(torch.autograd.Function):
             lease = _Lease()
             zout, log_s, bufs, _ = run_flowstep(dims, blob, plan, z, ctx_packed, prec, inverse, lease, need_bwd)
             if need_bwd:
+                # zout / log_s leave this function as outputs and get this node as grad_fn: keep storage-sharing
+                # aliases instead, or ctx -> output -> grad_fn -> ctx is a cycle only the cyclic GC can free
+                bufs = dict(bufs, zout=zout.detach(), log_s=log_s.detach())
                 saved[i] = (blob, bufs, lease, ws[i * n_per_flow:(i + 1) * n_per_flow],
                             None if sinks is None else sinks[i * n_per_flow:(i + 1) * n_per_flow])
             else:
