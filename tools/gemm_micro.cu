@@ -1,0 +1,151 @@
+// Micro-benchmark of the tcgen05 row GEMM engine (radtts_b200/csrc/rowgemm_tc.cuh) outside the library: the SAME
+// kernel template, launched with an explicit tile width and grid, on WN-shaped problems.  It answers the planning
+// questions DESIGN.md 9.1 leaves open in one GPU call:
+//   * time per tile as a function of the tile width BN (is a narrower tile proportionally cheaper, or is the MMA rate
+//     operand-fetch bound below BN = 256?)  -> whether wave-balanced tile widths can remove the 2.3-waves-in-3 loss;
+//   * time of exactly 1, 2, 3 full waves -> the in-tile rate with no quantisation;
+//   * the K = 1024 GEMMs (res_skip), where the epilogue rather than the MMAs sets the tile time.
+// Every configuration is checked on sampled outputs against a double-precision host reference.
+//
+// Build (no GPU needed):  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo \
+//                              -o tools/_bin/gemm_micro tools/gemm_micro.cu
+// Run on the GPU box:     tools/_bin/gemm_micro            (prints one line per configuration)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../radtts_b200/csrc/rowgemm_tc.cuh"
+
+namespace rb {
+long long g_launches = 0;   // the library defines this in capi.cu
+
+// bias + softplus + bf16 store: the arithmetic of the in_layer epilogue without the frame-plan lookups
+struct EpiMicro {
+  __nv_bfloat16* out; int ldo;
+  const float* bias;
+  __device__ __forceinline__ RowState prep(int) const { return RowState{true, 1.f}; }
+  __device__ __forceinline__ const float* colvec() const { return bias; }
+  template <int W>
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState&,
+                                             const float (&cv)[W]) const {
+    float y[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) y[i] = softplus_t<__nv_bfloat16>(acc[i] + cv[i]);
+    Act<__nv_bfloat16>::template stv<W>(out + (size_t)row * ldo + col0, y);
+  }
+};
+
+// launch_rowgemm_tc with the two knobs exposed
+static int launch_micro(const GemmDesc& d, const EpiMicro& epi, int bn, int grid, cudaStream_t st) {
+  TcParams p{};
+  p.nseg = d.nseg; p.N = d.N; p.rows_alloc = d.rows_alloc; p.plan = nullptr;
+  p.bn = bn; p.n_tiles_n = ceil_div(d.N, bn);
+  RB_TRY(make_map_bf16(d.seg[0].a, d.seg[0].lda, d.seg[0].lda, d.rows_alloc, kTcBM, &p.amap[0]));
+  for (int i = 1; i < kTcMaxMaps; ++i) p.amap[i] = p.amap[0];
+  for (int s = 0; s < d.nseg; ++s) p.seg[s] = TcSeg{0, d.seg[s].shift, d.seg[s].kcol, d.seg[s].klen / kTcBK};
+  RB_TRY(make_map_bf16(d.w, d.ldw, d.ldw, d.N, bn, &p.wmap));
+  RB_CUDA(cudaFuncSetAttribute(rowgemm_tc_kernel<EpiMicro>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  rowgemm_tc_kernel<EpiMicro><<<grid, kTcThreads, kTcSmemBytes, st>>>(p, epi);
+  return after_launch();
+}
+}  // namespace rb
+
+static float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+struct Problem {
+  int rows, C, N, taps, dil;   // A [rows][C]; K = taps * C; out [rows][N]
+};
+
+int main(int argc, char** argv) {
+  using namespace rb;
+  const int reps = argc > 1 ? atoi(argv[1]) : 20;
+  cudaStream_t st;
+  cudaStreamCreate(&st);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  // L2 flush buffer (larger than the 126 MB L2), written between timed launches
+  const size_t flush_bytes = 256u << 20;
+  void* flush; cudaMalloc(&flush, flush_bytes);
+
+  std::vector<Problem> probs;
+  // in_layer, cfg2-sized: 85 row tiles (the benchmarked batch), then exactly 1 / 2 / 3 waves at BN = 256 (N = 1024 -> 4
+  // column tiles: 37, 74, 111 row tiles)
+  for (int tiles_m : {85, 37, 74, 111}) probs.push_back({tiles_m * 128, 1024, 1024, 5, 2});
+  probs.push_back({85 * 128, 1024, 1024, 1, 1});   // res_skip: K = 1024
+  const int bns[] = {256, 240, 224, 208, 192, 176, 160, 144, 128, 96, 64};
+
+  for (const Problem& pr : probs) {
+    const int K = pr.taps * pr.C;
+    std::vector<__nv_bfloat16> hA((size_t)pr.rows * pr.C), hW((size_t)pr.N * K);
+    std::vector<float> hb(pr.N);
+    uint32_t s = 12345u + pr.rows;
+    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xffff) / 65536.f - 0.5f; };
+    for (auto& v : hA) v = __float2bfloat16(rnd());
+    for (auto& v : hW) v = __float2bfloat16(rnd() * 0.05f);
+    for (auto& v : hb) v = rnd();
+    __nv_bfloat16 *dA, *dW, *dO; float* db;
+    cudaMalloc(&dA, hA.size() * 2); cudaMalloc(&dW, hW.size() * 2); cudaMalloc(&dO, (size_t)pr.rows * pr.N * 2);
+    cudaMalloc(&db, pr.N * 4);
+    cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(dW, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, hb.data(), pr.N * 4, cudaMemcpyHostToDevice);
+    GemmDesc d{};
+    d.nseg = pr.taps; d.w = dW; d.ldw = K; d.N = pr.N; d.rows_alloc = pr.rows; d.plan = nullptr;
+    for (int t = 0; t < pr.taps; ++t) d.seg[t] = Seg{dA, pr.C, (t - pr.taps / 2) * pr.dil, 0, pr.C};
+    EpiMicro epi{dO, pr.N, db};
+    const double flops = 2.0 * pr.rows * pr.N * K;
+
+    for (int bn : bns) {
+      if (pr.taps == 1 && bn < 128) continue;
+      const int tiles = (pr.rows / 128) * ceil_div(pr.N, bn);
+      const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+      cudaMemsetAsync(dO, 0, (size_t)pr.rows * pr.N * 2, st);
+      int rc = launch_micro(d, epi, bn, grid, st);
+      if (rc || cudaStreamSynchronize(st) != cudaSuccess) {
+        printf("rows %d K %d N %d bn %d: launch failed rc=%d (%s)\n", pr.rows, K, pr.N, bn, rc,
+               cudaGetErrorString(cudaGetLastError()));
+        return 1;
+      }
+      // sampled check against a double-precision reference of the same bf16 inputs
+      std::vector<__nv_bfloat16> hO((size_t)pr.rows * pr.N);
+      cudaMemcpy(hO.data(), dO, hO.size() * 2, cudaMemcpyDeviceToHost);
+      double max_err = 0;
+      for (int i = 0; i < 96; ++i) {
+        const int r = i < 8 ? i : (i < 16 ? pr.rows - 1 - (i - 8) : (int)((i * 2654435761u) % (uint32_t)pr.rows));
+        const int c = i < 4 ? pr.N - 1 - i : (int)((i * 40503u + 7u) % (uint32_t)pr.N);
+        double acc = hb[c];
+        for (int t = 0; t < pr.taps; ++t) {
+          const int rr = r + (t - pr.taps / 2) * pr.dil;
+          if (rr < 0 || rr >= pr.rows) continue;
+          for (int k = 0; k < pr.C; ++k)
+            acc += (double)__bfloat162float(hA[(size_t)rr * pr.C + k]) *
+                   (double)__bfloat162float(hW[(size_t)c * K + t * pr.C + k]);
+        }
+        const double want = acc > 20 ? acc : log1p(exp(acc));
+        const double got = __bfloat162float(hO[(size_t)r * pr.N + c]);
+        const double err = fabs(got - want) / (fabs(want) + 1e-2);
+        if (err > max_err) max_err = err;
+      }
+      float total = 0;
+      for (int it = 0; it < reps + 3; ++it) {
+        cudaMemsetAsync(flush, it, flush_bytes, st);
+        cudaEventRecord(e0, st);
+        launch_micro(d, epi, bn, grid, st);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (it >= 3) total += ms;
+      }
+      const double us = total / reps * 1e3;
+      const int rounds = ceil_div(tiles, grid);
+      printf("rows %6d K %5d N %4d | bn %3d tiles %4d grid %3d rounds %d | %8.2f us  %7.1f TFLOP/s | us/round %6.2f "
+             "us/round/256col %6.2f | max rel err %.4f %s\n",
+             pr.rows, K, pr.N, bn, tiles, grid, rounds, us, flops / us * 1e-6, us / rounds, us / rounds * 256.0 / bn,
+             max_err, max_err < 2e-2 ? "ok" : "MISMATCH");
+      fflush(stdout);
+    }
+    cudaFree(dA); cudaFree(dW); cudaFree(dO); cudaFree(db);
+  }
+  (void)bf16_round;
+  return 0;
+}
