@@ -268,6 +268,7 @@ def run_reference(args):
             "ms_per_step": cb["ms_per_step_sample"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32", "data": "synthetic", "config": workload_config(args), "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": "mel frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line["config"]["global_batch"] = args.batch * max(1, args.gpus)   # the arm's config is the GPU arm's, key for key
     print(json.dumps(line))
 
 
