@@ -8,6 +8,24 @@ import torch
 from . import loss as rloss
 
 
+def bulk_first_order(model):
+    """Flat-buffer order of the trainable parameters for data parallelism: the decoder flows' parameter networks first
+    (94 % of the bytes; their gradients are final when the flow stack's backward returns), everything else after --
+    two contiguous all-reduce regions.  Returns (parameters in that order, number of flat-buffer ELEMENTS of the first
+    region, every tensor padded to a multiple of 4 elements exactly as FusedRAdam lays the buffer out)."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    bulk_ids, bulk = set(), []
+    for f in model.flows:
+        tfn = getattr(f, "affine_tfn", None)
+        net = getattr(tfn, "affine_param_predictor", None)
+        for p in ([] if net is None else net.parameters()):
+            if p.requires_grad and id(p) not in bulk_ids:
+                bulk_ids.add(id(p))
+                bulk.append(p)
+    ordered = bulk + [p for p in params if id(p) not in bulk_ids]
+    return ordered, sum((p.numel() + 3) // 4 * 4 for p in bulk)
+
+
 class TrainStep:
     def __init__(self, model, loss_weights, lr=1e-4, weight_decay=1e-6, grad_clip_val=1.0, bf16=True,
                  binarize_attention=True, use_binarization_loss=True, ddp=False, device_ids=None, capturable=False,
@@ -39,18 +57,7 @@ class TrainStep:
         params = [p for p in model.parameters() if p.requires_grad]
         self.n_bulk = 0
         if ddp and fused_optimizer and hasattr(model, "flows"):
-            # flat-buffer order: the decoder flows' parameter networks first (94 % of the bytes; their gradients are
-            # final when the flow stack's backward returns), everything else after -- two contiguous all-reduce regions
-            bulk_ids, bulk = set(), []
-            for f in model.flows:
-                tfn = getattr(f, "affine_tfn", None)
-                net = getattr(tfn, "affine_param_predictor", None)
-                for p in ([] if net is None else net.parameters()):
-                    if p.requires_grad and id(p) not in bulk_ids:
-                        bulk_ids.add(id(p))
-                        bulk.append(p)
-            params = bulk + [p for p in params if id(p) not in bulk_ids]
-            self.n_bulk = sum((p.numel() + 3) // 4 * 4 for p in bulk)
+            params, self.n_bulk = bulk_first_order(model)
         self.capturable = bool(capturable)
         self.fused_optimizer = bool(fused_optimizer)
         if self.fused_optimizer:

@@ -71,3 +71,66 @@ def test_two_rank_gloo_gradient_averaging_and_reductions():
     assert err < 1e-6
     assert mx == 11.0 and sm == 300.0
     assert len(sizes) >= 2   # more than one bucket was exercised
+
+
+def test_bulk_first_order_is_a_permutation_with_the_flow_networks_in_front():
+    """trainer.bulk_first_order: the flat gradient buffer of the data-parallel step is [flow WN parameters | rest]; the
+    first region is what the trainer all-reduces while the rest of the backward pass still runs."""
+    from radtts_b200 import configs
+    from radtts_b200.radtts import RADTTS
+    from radtts_b200.trainer import bulk_first_order
+    torch.manual_seed(0)
+    model = RADTTS(**configs.model_config("radtts"))
+    ordered, n_bulk = bulk_first_order(model)
+    trainable = [p for p in model.parameters() if p.requires_grad]
+    assert len(ordered) == len(trainable) and {id(p) for p in ordered} == {id(p) for p in trainable}
+    wn_ids = {id(p) for f in model.flows for p in f.affine_tfn.affine_param_predictor.parameters()}
+    k = len(wn_ids)
+    assert {id(p) for p in ordered[:k]} == wn_ids                      # the front region is exactly the flow networks
+    assert n_bulk == sum((p.numel() + 3) // 4 * 4 for p in ordered[:k])   # FusedRAdam's 16-byte padded layout
+    total = sum((p.numel() + 3) // 4 * 4 for p in ordered)
+    assert 0.9 < n_bulk / total < 0.97                                  # "94 % of the bytes"
+    rest = [p for p in trainable if id(p) not in wn_ids]
+    assert [id(p) for p in ordered[k:]] == [id(p) for p in rest]       # the remainder keeps module order
+
+
+def _two_region_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    parallel.init_from_env("gloo")
+    # the trainer's exchange on a flat buffer: SUM all-reduce of [0, n_bulk) and of [n_bulk, end) in chunks, the mean
+    # and the clip coefficient folded into one scale (trainer._allreduce / _update)
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(10_000, generator=g)
+    mine = flat.clone()
+    n_bulk, chunk = 6_400, 3_000
+    for c in flat[:n_bulk].split(chunk):
+        dist.all_reduce(c)
+    for c in flat[n_bulk:].split(chunk):
+        dist.all_reduce(c)
+    clip = 0.5
+    norm = torch.linalg.vector_norm(flat) / world
+    scale = (clip / (norm + 1e-6)).clamp(max=1.0) / world
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    mean = sum(gathered) / world
+    want = mean * (clip / (torch.linalg.vector_norm(mean) + 1e-6)).clamp(max=1.0)   # clip_grad_norm_ on the mean
+    if rank == 0:
+        out.put(float((flat * scale - want).abs().max()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_gloo_two_region_sum_with_folded_mean_and_clip():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_two_region_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = out.get(timeout=100)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-6
