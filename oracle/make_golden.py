@@ -84,6 +84,14 @@ def _param_summary(t):
     return np.array([f.sum().item(), f.norm().item()], dtype=np.float64), f[::1009][:64].float().numpy()
 
 
+def grad_samples(t):
+    """64 strided values of a gradient tensor (the whole tensor when it has <= 64 elements), zero-padded to 64: the
+    fixture side of the elementwise gradient checks in tests/_gradcheck.py (same indexing there)."""
+    f = t.detach().flatten()
+    sp = f[::max(1, f.numel() // 64)][:64].float().numpy()
+    return np.pad(sp, (0, 64 - len(sp)))
+
+
 def gen_radtts_forward(ns):
     """config_ljs_radtts: full RADTTS.forward (eval mode) with binarize_attention=True, the RADTTSLoss terms,
     then -- on the captured decoder inputs -- the decoder loop's gradients and the sampling direction."""
@@ -200,6 +208,7 @@ def gen_radtts_forward_soft(ns):
     g["grad_names"] = np.array(names)
     g["grad_sums"] = np.stack(sums)
     g["grad_samples"] = np.stack(samples)
+    g["grad_strided"] = np.stack([grad_samples(p.grad) for k, p in model.named_parameters() if p.grad is not None])
     np.savez_compressed(os.path.join(GOLD, "radtts_forward_soft.npz"), **g)
     print("wrote radtts_forward_soft.npz", os.path.getsize(os.path.join(GOLD, "radtts_forward_soft.npz")), "bytes;",
           "total %.5f, %d parameter gradients" % (g["total"], len(names)))
@@ -228,12 +237,13 @@ def gen_decoder_cfg_train(ns):
     total.backward()
     g = {"attn": out["attn"].detach().numpy(), "total": np.float32(total.item()),
          "loss_names": np.array(sorted(ld)), "loss_values": np.array([float(ld[k][0]) for k in sorted(ld)], dtype=np.float32)}
-    names, sums = [], []
+    names, sums, samples = [], [], []
     for k, p in model.named_parameters():
         if p.grad is not None:
-            names.append(k); sums.append(_param_summary(p.grad)[0])
+            names.append(k); sums.append(_param_summary(p.grad)[0]); samples.append(grad_samples(p.grad))
     g["grad_names"] = np.array(names)
     g["grad_sums"] = np.stack(sums)
+    g["grad_strided"] = np.stack(samples)
     np.savez_compressed(os.path.join(GOLD, "decoder_cfg_train.npz"), **g)
     print("wrote decoder_cfg_train.npz", os.path.getsize(os.path.join(GOLD, "decoder_cfg_train.npz")), "bytes;",
           "total %.5f, losses %s, %d gradients" % (g["total"], dict(zip(g["loss_names"], g["loss_values"])), len(names)))
@@ -259,15 +269,59 @@ def gen_radtts_train(ns):
     total.backward()
     g = {"attn": out["attn"].detach().numpy(), "total": np.float32(total.item()), "loss_bin": np.float32(bin_loss.item()),
          "loss_mel": np.float32(ld["loss_mel"][0].item()), "loss_ctc": np.float32(ld["loss_ctc"][0].item())}
-    names, sums = [], []
+    names, sums, samples = [], [], []
     for k, p in model.named_parameters():
         if p.grad is not None:
-            names.append(k); sums.append(_param_summary(p.grad)[0])
+            names.append(k); sums.append(_param_summary(p.grad)[0]); samples.append(grad_samples(p.grad))
     g["grad_names"] = np.array(names)
     g["grad_sums"] = np.stack(sums)
+    g["grad_strided"] = np.stack(samples)
     np.savez_compressed(os.path.join(GOLD, "radtts_train.npz"), **g)
     print("wrote radtts_train.npz", os.path.getsize(os.path.join(GOLD, "radtts_train.npz")), "bytes; total %.5f, %d gradients"
           % (g["total"], len(names)))
+
+
+def gen_cfg1(ns):
+    """BASELINE.json configs[0]: config_ljs_radtts, batch 4 x text 100 x 400 mel frames, in the regime bench.py steps
+    (binarize_attention=True; flow + CTC + binarization losses).  The unmodified reference's forward, RADTTSLoss and
+    backward in eval mode (fp32, CPU): outputs, loss terms, and for EVERY parameter gradient its (sum, norm) and 64
+    strided values."""
+    import torch
+    from radtts_b200 import synth
+    model, cfg, sd = _ref_model(ns, "config_ljs_radtts.json")
+    B, T1, T2 = 4, 400, 100
+    batch = synth.synth_batch(B, T1, T2, seed=20261)
+    model.zero_grad()
+    out = model(batch["mel"], batch["speaker_ids"], batch["text"], batch["in_lens"], batch["out_lens"],
+                binarize_attention=True, attn_prior=batch["attn_prior"])
+    g = {"z_mel": out["z_mel"].detach().numpy(),
+         "attn_packed": np.packbits(out["attn"].detach().numpy().astype(np.uint8), axis=None),
+         "attn_soft": out["attn_soft"].detach().numpy().astype(np.float16),      # checked at 2e-3 relative only
+         "attn_soft_sample": out["attn_soft"].detach().numpy()[:, :, ::7, ::3].copy(),
+         "attn_logprob_sample": out["attn_logprob"].detach().numpy()[:, :, ::7, ::3].copy(),
+         "log_det_W": np.array([float(x) for x in out["log_det_W_list"]], dtype=np.float32)}
+    for i in (0, 3, 7):
+        g["log_s_%d" % i] = out["log_s_list"][i].detach().numpy()
+    lw = cfg["train_config"]["loss_weights"]
+    crit = ns.loss.RADTTSLoss(sigma=1.0, n_group_size=2, loss_weights=lw)
+    ld = crit(out, batch["in_lens"], batch["out_lens"])
+    total = sum(v * w for v, w in ld.values() if w > 0)
+    bin_loss = ns.loss.AttentionBinarizationLoss()(out["attn"], out["attn_soft"])
+    total = total + bin_loss * lw["binarization_loss_weight"]
+    total.backward()
+    g.update(total=np.float32(total.item()), loss_bin=np.float32(bin_loss.item()),
+             loss_mel=np.float32(ld["loss_mel"][0].item()), loss_prior_mel=np.float32(ld["loss_prior_mel"][0].item()),
+             loss_ctc=np.float32(ld["loss_ctc"][0].item()))
+    names, sums, samples = [], [], []
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            names.append(k); sums.append(_param_summary(p.grad)[0]); samples.append(grad_samples(p.grad))
+    g["grad_names"] = np.array(names)
+    g["grad_sums"] = np.stack(sums)
+    g["grad_strided"] = np.stack(samples)
+    np.savez_compressed(os.path.join(GOLD, "cfg1_train.npz"), **g)
+    print("wrote cfg1_train.npz", os.path.getsize(os.path.join(GOLD, "cfg1_train.npz")), "bytes; total %.5f mel %.5f ctc "
+          "%.5f bin %.5f, %d gradients" % (g["total"], g["loss_mel"], g["loss_ctc"], g["loss_bin"], len(names)))
 
 
 def gen_bgap(ns):
@@ -391,7 +445,7 @@ def gen_radtts_infer(ns):
           {k: v.shape for k, v in g.items() if k.endswith("mel")})
 
 
-GENERATORS = {"mas": gen_mas, "radtts_infer": gen_radtts_infer, "radtts_forward_soft": gen_radtts_forward_soft, "decoder_cfg_train": gen_decoder_cfg_train, "radtts_train": gen_radtts_train, "radtts_forward": gen_radtts_forward, "bgap": gen_bgap,
+GENERATORS = {"cfg1": gen_cfg1, "mas": gen_mas, "radtts_infer": gen_radtts_infer, "radtts_forward_soft": gen_radtts_forward_soft, "decoder_cfg_train": gen_decoder_cfg_train, "radtts_train": gen_radtts_train, "radtts_forward": gen_radtts_forward, "bgap": gen_bgap,
               "decoder_cfg_forward": gen_decoder_cfg_forward}
 
 if __name__ == "__main__":

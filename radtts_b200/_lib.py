@@ -72,15 +72,8 @@ def require_cuda(*tensors):
             raise RadttsB200Error("radtts_b200 ops run on CUDA tensors only (got %s); no CPU fallback" % t.device)
 
 
-_ws_cache = {}
-
-
-def workspace(device, nbytes):
-    """Grow-only per-device scratch buffer (uint8)."""
-    nbytes = int(nbytes)
-    key = (device.type, device.index)
-    buf = _ws_cache.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _ws_cache[key] = buf
-    return buf
+def scratch(device, nbytes):
+    """Per-call scratch buffer (uint8) from torch's stream-ordered caching allocator.  Every user gets its OWN
+    allocation: kernels on different streams (MAS on the main stream, the prefetched CTC on a side stream) never share
+    one, and a CUDA-graph capture keeps its scratch alive in the graph's private pool."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

@@ -33,7 +33,7 @@ def mas_forward(attn, in_lens, out_lens, is_prob=True, return_indices=False):
     dur = torch.empty((B, T2), dtype=torch.int32, device=dev) if return_indices else None
     L = _lib.lib()
     nws = L.radtts_mas_workspace_bytes(B, T1, T2, int(bool(is_prob)))
-    ws = _lib.workspace(dev, nws)
+    ws = _lib.scratch(dev, nws)
     rc = L.radtts_mas_forward(_lib.ptr(attn), ctypes.c_int(int(bool(is_prob))), _lib.ptr(in_lens),
                               _lib.ptr(out_lens), B, T1, T2, _lib.ptr(hard), _lib.ptr(f2t), _lib.ptr(dur),
                               _lib.ptr(ws), ctypes.c_size_t(ws.numel()), _lib.stream_of(attn))

@@ -194,7 +194,6 @@ class ConvLSTMLinear(nn.Module):
             context = self._convs(context)
         if self.lstm_type != "":
             x = context.transpose(1, 2)
-            self.bilstm.flatten_parameters()
             if lens is not None:
                 packed = nn.utils.rnn.pack_padded_sequence(x, lens.long().cpu(), batch_first=True,
                                                            enforce_sorted=False)
@@ -213,7 +212,6 @@ def run_bilstm(lstm, x, lens):
     if lstm_ops.supported(lstm, x):
         return lstm_ops.bilstm(lstm, x, lens)
     packed = nn.utils.rnn.pack_padded_sequence(x, lens.long().cpu(), batch_first=True, enforce_sorted=False)
-    lstm.flatten_parameters()
     out, _ = nn.utils.rnn.pad_packed_sequence(lstm(packed)[0], batch_first=True, total_length=x.shape[1])
     return out
 
@@ -276,7 +274,6 @@ class Encoder(nn.Module):
             if lstm_ops.supported(self.lstm, x):
                 full = torch.full((x.shape[0],), x.shape[1], dtype=torch.int32, device=x.device)
                 return lstm_ops.bilstm(self.lstm, x, full)
-            self.lstm.flatten_parameters()
             return self.lstm(x)[0]
 
 

@@ -19,8 +19,9 @@ _forced_precision = None
 
 
 _direct_grad = False
-flow_backward_done = None   # optional callable(): invoked right after the flow stack's backward has enqueued its last
-                            # kernel (with direct accumulation on, every WN gradient is final in .grad at that point)
+flow_grads_ready = None     # optional callable(flow_index, final): invoked by the flow stack's backward right after the
+                            # last kernel producing flow `flow_index`'s parameter-network gradients has been enqueued;
+                            # final=True when every one of them went straight into .grad (direct accumulation)
 
 
 def set_direct_grad_accumulation(on):
@@ -30,6 +31,26 @@ def set_direct_grad_accumulation(on):
     fire, so only trainers that reduce gradients themselves (radtts_b200.trainer) switch it on."""
     global _direct_grad
     _direct_grad = bool(on)
+
+
+class trainer_scope:
+    """Context manager a trainer wraps around ITS forward + backward: direct gradient accumulation and the per-flow
+    `flow_grads_ready` callback are process-global switches, so they are set on entry and restored on exit -- another
+    TrainStep, or any other user of the flow stack in the same process, never inherits them."""
+
+    def __init__(self, direct_grad, on_flow_grads=None):
+        self.new = (bool(direct_grad), on_flow_grads)
+
+    def __enter__(self):
+        global _direct_grad, flow_grads_ready
+        self.prev = (_direct_grad, flow_grads_ready)
+        _direct_grad, flow_grads_ready = self.new
+        return self
+
+    def __exit__(self, *exc):
+        global _direct_grad, flow_grads_ready
+        _direct_grad, flow_grads_ready = self.prev
+        return False
 
 
 def set_precision(p):
@@ -277,24 +298,82 @@ def prepare_flow(dims, ws, prec, want_backward, device):
 
 class _Pool:
     """Zero-initialised scratch tensors, recycled across steps.  The kernels rely on every packed buffer being
-    FINITE beyond the rows they write (stale values are multiplied by zero rows; NaN garbage would not be)."""
+    FINITE beyond the rows they write (stale values are multiplied by zero rows; NaN garbage would not be).
 
-    def __init__(self):
-        self.free = {}
+    Bounded: free buffers are kept per exact shape in least-recently-used order and the oldest shapes are dropped once
+    the free bytes exceed `cap_bytes` (RADTTS_POOL_CAP_MB, default 8 GB of the 180 GB) -- variable-length training sees a
+    new `rows` for every distinct padded batch length.  Buffers created while a CUDA graph is being captured live in the
+    graph's private memory pool, warm eager buffers a capture takes over are pinned for the graph's lifetime, and both
+    go to a separate free list that `end_capture()` drops, so eager steps never write into memory a captured graph
+    replays on."""
+
+    def __init__(self, cap_bytes=None):
+        import collections
+        self.free = collections.OrderedDict()
+        self.cap_free = {}
+        self.pinned = []
+        self.free_bytes = 0
+        if cap_bytes is None:
+            cap_bytes = int(os.environ.get("RADTTS_POOL_CAP_MB", "8192")) << 20
+        self.cap_bytes = cap_bytes
+
+    @staticmethod
+    def _key(shape, dtype, device):
+        return (tuple(shape), dtype, device.type, device.index)
 
     def get(self, shape, dtype, device):
-        key = (tuple(shape), dtype, device.type, device.index)
+        key = self._key(shape, dtype, device)
+        if device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            lst = self.cap_free.get(key)
+            if lst:
+                return lst.pop()
+            lst = self.free.get(key)
+            if lst:
+                # a warm eager buffer (already zero-initialised: no memset node in the graph); from now on it belongs
+                # to captured graphs only and is kept alive for them
+                t = lst.pop()
+                self.free_bytes -= t.numel() * t.element_size()
+                if not lst:
+                    del self.free[key]
+                self.pinned.append(t)
+            else:
+                t = torch.zeros(shape, dtype=dtype, device=device)
+            t._rb_captured = True
+            return t
         lst = self.free.get(key)
         if lst:
-            return lst.pop()
+            t = lst.pop()
+            self.free_bytes -= t.numel() * t.element_size()
+            if not lst:
+                del self.free[key]
+            else:
+                self.free.move_to_end(key)
+            return t
         return torch.zeros(shape, dtype=dtype, device=device)
 
     def put(self, t):
-        key = (tuple(t.shape), t.dtype, t.device.type, t.device.index)
+        key = self._key(t.shape, t.dtype, t.device)
+        if getattr(t, "_rb_captured", False):
+            self.cap_free.setdefault(key, []).append(t)
+            return
         self.free.setdefault(key, []).append(t)
+        self.free.move_to_end(key)
+        self.free_bytes += t.numel() * t.element_size()
+        while self.free_bytes > self.cap_bytes and len(self.free) > 1:
+            old_key = next(iter(self.free))
+            if old_key == key:
+                break
+            for old in self.free.pop(old_key):
+                self.free_bytes -= old.numel() * old.element_size()
+
+    def end_capture(self):
+        self.cap_free.clear()
 
     def clear(self):
         self.free.clear()
+        self.cap_free.clear()
+        self.pinned = []
+        self.free_bytes = 0
 
 
 POOL = _Pool()
@@ -866,7 +945,7 @@ class _AttnCTCFn(torch.autograd.Function):
         grad = torch.empty_like(x)
         L = _lib.lib()
         nws = int(L.radtts_attn_ctc_workspace_bytes(B, T1, T2))
-        ws = _lib.workspace(dev, nws)
+        ws = _lib.scratch(dev, nws)
         _lib.check(L.radtts_attn_ctc(_lib.ptr(x), _lib.ptr(il), _lib.ptr(ol), B, T1, T2, ctypes.c_float(blank_logprob),
                                      _lib.ptr(losses), _lib.ptr(grad), _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
                                      _lib.stream_of(x)), "radtts_attn_ctc")

@@ -112,12 +112,16 @@ def flow_stack_backward(saved, g_zout, g_log_s):
                 if t is not None and sk is not None and sk.grad is not None and sk.grad.dtype == t.dtype:
                     sk.grad.add_(t.reshape(sk.grad.shape))
                     out[j] = None
+        final = direct
         for j, t in enumerate(out):
             if t is not None:
                 assert t.numel() == int(torch.Size(w_shapes[base + j]).numel()), (j, t.shape, w_shapes[base + j])
                 grads[base + j] = t.reshape(w_shapes[base + j])
+                if j > 0:
+                    final = False      # a parameter-network gradient still has to go through AccumulateGrad
+        if ops.flow_grads_ready is not None:
+            # flows finish in the order n-1 .. 0: a data-parallel trainer starts this flow's all-reduce right here
+            ops.flow_grads_ready(i, final)
         g_z = g_zin
-    if ops.flow_backward_done is not None:
-        ops.flow_backward_done()
     g_ctx_out = g_ctx if ctx_dtype == torch.float32 else g_ctx.to(ctx_dtype)
     return (g_z, g_ctx_out, None, None, None, None, None, None) + tuple(grads)

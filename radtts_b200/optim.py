@@ -48,7 +48,19 @@ class FusedRAdam:
         total_norm = torch.linalg.vector_norm(self.grad)
         return (max_norm / (total_norm + 1e-6)).clamp(max=1.0).reshape(1)
 
+    def check_views(self):
+        """Every parameter must still be a view of the flat buffer (nn.LSTM.flatten_parameters() and `p.data = ...`
+        re-point storage silently; the fused kernel would then update memory nobody reads)."""
+        off = 0
+        for p in self.params:
+            if p.data_ptr() != self.flat.data_ptr() + off * 4:
+                raise _lib.RadttsB200Error("FusedRAdam: a parameter of shape %s no longer lives in the flat buffer "
+                                           "(was flatten_parameters() or `.data =` applied to it?)" % (tuple(p.shape),))
+            off += (p.numel() + 3) // 4 * 4
+
     def step(self, grad_scale=None):
+        if not torch.cuda.is_current_stream_capturing():
+            self.check_views()
         L = _lib.lib()
         b1, b2 = self.betas
         _lib.check(L.radtts_radam_step(_lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg),

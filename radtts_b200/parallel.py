@@ -43,37 +43,64 @@ def reduce_scalar(x, op="max", device=None):
     return float(t.item())
 
 
-def allreduce_mean_grads(params, bucket_bytes=128 << 20, async_op=False):
-    """Bucketed gradient averaging: gradients are flattened into <= bucket_bytes buffers (per dtype, in parameter
-    order), all-reduced and copied back.  The reference does the same with ONE flat 904 MB buffer after backward
-    (distributed.py:133-140); buckets let NCCL start on the first flows' gradients while later buckets are packed."""
+def flow_first_order(model):
+    """Flat-buffer order of the trainable parameters for data parallelism: the decoder flows' parameter networks first,
+    flow by flow (94 % of the bytes; flow i's gradients are final as soon as ITS backward has run, and the flows finish in
+    the order n-1 .. 0), everything else after.  Returns (parameters in that order, [(lo, hi)] flat-buffer ELEMENT range
+    of every flow's region in flow order); every tensor is padded to a multiple of 4 elements exactly as FusedRAdam lays
+    the buffer out, so regions[-1][1] is where the remainder starts."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    seen, ordered, regions, off = set(), [], [], 0
+    for f in getattr(model, "flows", []):
+        tfn = getattr(f, "affine_tfn", None)
+        net = getattr(tfn, "affine_param_predictor", None)
+        lo = off
+        for p in ([] if net is None else net.parameters()):
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                ordered.append(p)
+                off += (p.numel() + 3) // 4 * 4
+        regions.append((lo, off))
+    ordered += [p for p in params if id(p) not in seen]
+    return ordered, regions
+
+
+def allreduce_flat(flat, regions=(), ready=None, comm_stream=None, chunk_elems=32 << 20):
+    """SUM all-reduce of the flat gradient buffer (the reference does ONE flat call after backward,
+    distributed.py:133-140; the mean is folded into the optimizer's scale).  `regions` = [(lo, hi)] element ranges whose
+    gradients become final early, listed in the order they do; ready[i] = a CUDA event recorded when region i is final,
+    True (final, nothing to wait for -- CPU / gloo tests) or None (not tracked: reduced with the remainder).  Ready
+    regions are reduced first -- on `comm_stream` as their events fire, i.e. underneath the rest of the backward pass --
+    and everything else follows on the current stream.  Chunks of `chunk_elems` let NCCL pipeline over NVLink / NVSwitch.
+    Returns the number of collective calls."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return []
-    world = dist.get_world_size()
-    buckets, cur, cur_bytes, cur_dtype = [], [], 0, None
-    for p in params:
-        if p.grad is None:
-            continue
-        nb = p.grad.numel() * p.grad.element_size()
-        if cur and (cur_bytes + nb > bucket_bytes or p.grad.dtype != cur_dtype):
-            buckets.append(cur)
-            cur, cur_bytes = [], 0
-        cur.append(p)
-        cur_bytes += nb
-        cur_dtype = p.grad.dtype
-    if cur:
-        buckets.append(cur)
-    pending = []
-    for bucket in buckets:
-        flat = torch.cat([p.grad.reshape(-1) for p in bucket])
-        work = dist.all_reduce(flat, async_op=True)
-        pending.append((work, flat, bucket))
-    for work, flat, bucket in pending:
-        work.wait()
-        flat.div_(world)
-        off = 0
-        for p in bucket:
-            n = p.grad.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p.grad))
-            off += n
-    return [len(b) for b in buckets]
+        return 0
+    n_calls = 0
+    ready = list(ready) if ready is not None else [None] * len(regions)
+    early = [(r, ev) for r, ev in zip(regions, ready) if ev is not None and r[1] > r[0]]
+
+    def reduce_range(lo, hi):
+        n = 0
+        for chunk in flat[lo:hi].split(chunk_elems):
+            dist.all_reduce(chunk)
+            n += 1
+        return n
+
+    if early and comm_stream is not None:
+        cur = torch.cuda.current_stream(flat.device)
+        with torch.cuda.stream(comm_stream):
+            for (lo, hi), ev in early:
+                if ev is not True:
+                    comm_stream.wait_event(ev)
+                n_calls += reduce_range(lo, hi)
+    else:
+        for (lo, hi), _ in early:
+            n_calls += reduce_range(lo, hi)
+    pos = 0          # the remainder: the gaps between the early ranges
+    for lo, hi in sorted(r for r, _ in early) + [(flat.numel(), flat.numel())]:
+        if lo > pos:
+            n_calls += reduce_range(pos, lo)
+        pos = max(pos, hi)
+    if early and comm_stream is not None:
+        cur.wait_stream(comm_stream)
+    return n_calls

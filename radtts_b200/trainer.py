@@ -6,30 +6,20 @@ import os
 import torch
 
 from . import loss as rloss
+from . import parallel
 
 
 def bulk_first_order(model):
-    """Flat-buffer order of the trainable parameters for data parallelism: the decoder flows' parameter networks first
-    (94 % of the bytes; their gradients are final when the flow stack's backward returns), everything else after --
-    two contiguous all-reduce regions.  Returns (parameters in that order, number of flat-buffer ELEMENTS of the first
-    region, every tensor padded to a multiple of 4 elements exactly as FusedRAdam lays the buffer out)."""
-    params = [p for p in model.parameters() if p.requires_grad]
-    bulk_ids, bulk = set(), []
-    for f in model.flows:
-        tfn = getattr(f, "affine_tfn", None)
-        net = getattr(tfn, "affine_param_predictor", None)
-        for p in ([] if net is None else net.parameters()):
-            if p.requires_grad and id(p) not in bulk_ids:
-                bulk_ids.add(id(p))
-                bulk.append(p)
-    ordered = bulk + [p for p in params if id(p) not in bulk_ids]
-    return ordered, sum((p.numel() + 3) // 4 * 4 for p in bulk)
+    """(parameters in data-parallel flat-buffer order, ELEMENTS of the flow-network region in front) -- see
+    parallel.flow_first_order, which also gives the per-flow sub-ranges."""
+    ordered, regions = parallel.flow_first_order(model)
+    return ordered, (regions[-1][1] if regions else 0)
 
 
 class TrainStep:
     def __init__(self, model, loss_weights, lr=1e-4, weight_decay=1e-6, grad_clip_val=1.0, bf16=True,
                  binarize_attention=True, use_binarization_loss=True, ddp=False, device_ids=None, capturable=False,
-                 fused_optimizer=True):
+                 fused_optimizer=True, probe_batch=None, loss_kwargs=None):
         self.raw_model = model
         self.model = model
         self.world = 1
@@ -43,7 +33,8 @@ class TrainStep:
                 # replicas start identical (reference distributed.py:111-114 broadcasts every tensor from rank 0)
                 for t in list(model.parameters()) + list(model.buffers()):
                     dist.broadcast(t.data, 0)
-        self.criterion = rloss.RADTTSLoss(sigma=1.0, n_group_size=model.n_group_size, loss_weights=loss_weights)
+        self.criterion = rloss.RADTTSLoss(sigma=1.0, n_group_size=getattr(model, "n_group_size", 1),
+                                          loss_weights=loss_weights, **(loss_kwargs or {}))
         self.bin_loss = rloss.AttentionBinarizationLoss()
         if next(model.parameters()).is_cuda and hasattr(model, "attention"):
             # launch the attention CTC kernel as soon as ConvAttention is done, on a side stream (captured as a parallel
@@ -54,26 +45,36 @@ class TrainStep:
         self.binarize = binarize_attention
         self.use_bin_loss = use_binarization_loss
         self.grad_clip_val = grad_clip_val
-        params = [p for p in model.parameters() if p.requires_grad]
-        self.n_bulk = 0
-        if ddp and fused_optimizer and hasattr(model, "flows"):
-            params, self.n_bulk = bulk_first_order(model)
         self.capturable = bool(capturable)
         self.fused_optimizer = bool(fused_optimizer)
+        self.comm = None
+        self.flow_regions = []
+        self.ev_flow = []
+        self._flow_final = []
+        params = [p for p in model.parameters() if p.requires_grad]
+        if ddp and fused_optimizer and hasattr(model, "flows"):
+            params, self.flow_regions = parallel.flow_first_order(model)
+        if probe_batch is not None:
+            # the reference optimizer skips parameters whose .grad is None (radam.py:53-55) -- e.g. v_pred_module /
+            # v_embeddings in decoder-only training.  One plain forward/backward finds them; they stay out of the flat
+            # buffer, so neither weight decay nor the moment updates touch them.
+            used = self._probe_used(probe_batch)
+            params = [p for p in params if id(p) in used]
+            if self.flow_regions:
+                assert all(id(p) in used for f in model.flows for p in f.affine_tfn.affine_param_predictor.parameters())
         if self.fused_optimizer:
-            from . import ops
             from .optim import FusedRAdam
             self.optimizer = FusedRAdam(params, lr=lr, weight_decay=weight_decay)
-            # gradients live in the optimizer's flat buffer and this class reduces them itself (no DDP hooks): let
-            # the flow stack's backward add weight_v / weight_g gradients straight into it
-            ops.set_direct_grad_accumulation(True)
-            if self.world > 1 and self.n_bulk > 0 and not os.environ.get("RADTTS_NO_COMM_OVERLAP"):
+            # gradients live in the optimizer's flat buffer and this class reduces them itself (no DDP hooks): the flow
+            # stack's backward adds weight_v / weight_g gradients straight into it (ops.trainer_scope in _fwd_bwd)
+            if self.world > 1 and self.flow_regions and not os.environ.get("RADTTS_NO_COMM_OVERLAP"):
                 dev = next(model.parameters()).device
                 self.comm = torch.cuda.Stream(device=dev)
-                # external: inside the captured step this becomes an event-record NODE that the eagerly launched NCCL
-                # all-reduce (comm stream) can wait on -- the collective then overlaps the rest of the backward graph
-                self.ev_bulk = torch.cuda.Event(external=True)
-                ops.flow_backward_done = lambda: self.ev_bulk.record(torch.cuda.current_stream(dev))
+                # external: inside the captured step these become event-record NODES that the eagerly launched NCCL
+                # all-reduces (comm stream) wait on -- flow i's region is reduced while the graph is still running the
+                # backward of flows i-1 .. 0, the LSTMs, the attention and the encoder
+                self.ev_flow = [torch.cuda.Event(external=True) for _ in self.flow_regions]
+                self._flow_final = [False] * len(self.flow_regions)
         else:
             self.optimizer = torch.optim.RAdam(params, lr=lr, weight_decay=weight_decay, foreach=True,
                                                capturable=self.capturable)
@@ -82,6 +83,21 @@ class TrainStep:
         self.launches_per_replay = 0
         self.static_batch = None
         self.static_loss = None
+
+    def _probe_used(self, batch):
+        self.raw_model.zero_grad(set_to_none=True)
+        total, _ = self.forward_loss(batch)
+        total.backward()
+        used = {id(p) for p in self.raw_model.parameters() if p.grad is not None}
+        self.raw_model.zero_grad(set_to_none=True)
+        self.criterion.attn_ctc_loss._prefetched = None
+        return used
+
+    def _on_flow_grads(self, i, final):
+        if i < len(self.ev_flow):
+            self._flow_final[i] = bool(final)
+            if final:
+                self.ev_flow[i].record(torch.cuda.current_stream(self.optimizer.grad.device))
 
     def forward_loss(self, batch):
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.bf16):
@@ -128,6 +144,8 @@ class TrainStep:
             with torch.cuda.graph(self.graph_update, pool=graph.pool()):
                 self._update()
         self.launches_per_replay = _lib.launch_count() - n0   # kernels of libradtts_b200.so inside one replay
+        from . import ops
+        ops.POOL.end_capture()
 
     def step(self, batch):
         if self.graph is not None:
@@ -141,31 +159,21 @@ class TrainStep:
         return self._eager_step(batch)
 
     def _fwd_bwd(self, batch):
+        from . import ops
         self.optimizer.zero_grad(set_to_none=not self.fused_optimizer)
-        total, _ = self.forward_loss(batch)
-        total.backward()
+        with ops.trainer_scope(self.fused_optimizer, self._on_flow_grads if self.ev_flow else None):
+            total, _ = self.forward_loss(batch)
+            total.backward()
         return total.detach()
 
     def _allreduce(self):
-        # data-parallel gradient exchange on the flat buffer: the reference does one flat all-reduce after backward
-        # (distributed.py:133-140); 128 MB chunks let NCCL pipeline over NVLink / NVSwitch.  The flow stack's region
-        # (first n_bulk elements) is reduced on the comm stream as soon as ev_bulk fires, i.e. while the LSTM /
-        # attention / encoder part of the backward pass is still running; the remainder follows at the end.
-        import torch.distributed as dist
-        g = self.optimizer.grad
-        n_bulk = self.n_bulk if getattr(self, "comm", None) is not None else 0
-        if n_bulk > 0:
-            cur = torch.cuda.current_stream(g.device)
-            with torch.cuda.stream(self.comm):
-                self.comm.wait_event(self.ev_bulk)
-                for chunk in g[:n_bulk].split(32 << 20):
-                    dist.all_reduce(chunk)
-            for chunk in g[n_bulk:].split(32 << 20):
-                dist.all_reduce(chunk)
-            cur.wait_stream(self.comm)
-        else:
-            for chunk in g.split(32 << 20):
-                dist.all_reduce(chunk)
+        # data-parallel gradient exchange on the flat buffer (parallel.allreduce_flat): flow i's region is reduced on
+        # the comm stream as soon as ITS event fires (flows finish 7 .. 0), underneath the rest of the backward pass;
+        # the non-flow remainder (6 % of the bytes) follows at the end.  Regions whose gradients did not all take the
+        # direct route (a frozen parameter, a non-fp32 .grad) are not final at their event and go with the remainder.
+        order = list(reversed(range(len(self.flow_regions))))
+        ready = [self.ev_flow[i] if (self.ev_flow and self._flow_final[i]) else None for i in order]
+        parallel.allreduce_flat(self.optimizer.grad, [self.flow_regions[i] for i in order], ready, self.comm)
 
     def _update(self):
         if self.grad_clip_val > 0:

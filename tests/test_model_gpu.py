@@ -8,6 +8,7 @@ import torch
 
 from radtts_b200 import configs, loss as rloss, ops, synth
 from radtts_b200.radtts import RADTTS
+from _gradcheck import check_param_grads
 
 pytestmark = pytest.mark.gpu
 
@@ -209,16 +210,7 @@ def test_soft_attention_training_direction_matches_reference(golden_dir, cuda_li
     assert abs(float(losses["loss_mel"][0]) - float(g["loss_mel"])) < 1e-3 * abs(float(g["loss_mel"]))
     assert abs(float(losses["loss_ctc"][0]) - float(g["loss_ctc"])) < 1e-3 * abs(float(g["loss_ctc"]))
     assert abs(float(total) - float(g["total"])) < 1e-3 * abs(float(g["total"]))
-    params = dict(m.named_parameters())
-    bad = []
-    for name, summ in zip(g["grad_names"], g["grad_sums"]):
-        p = params[str(name)]
-        if p.grad is None:
-            bad.append((str(name), "no grad"))
-            continue
-        norm = float(p.grad.double().norm())
-        if abs(norm - summ[1]) > 5e-3 * summ[1] + 1e-7:
-            bad.append((str(name), norm, float(summ[1])))
+    bad = check_param_grads(dict(m.named_parameters()), g)     # norm AND 64 strided values per parameter
     assert not bad, bad[:8]
 
 
@@ -255,16 +247,7 @@ def test_decoder_config_training_gradients_match_reference(golden_dir, cuda_lib)
         got = float(losses[str(name)][0])
         assert abs(got - float(want)) < 1e-3 * abs(float(want)) + 1e-6, (str(name), got, float(want))
     assert abs(float(total) - float(g["total"])) < 1e-3 * abs(float(g["total"]))
-    params = dict(m.named_parameters())
-    bad = []
-    for name, summ in zip(g["grad_names"], g["grad_sums"]):
-        p = params[str(name)]
-        if p.grad is None:
-            bad.append((str(name), "no grad"))
-            continue
-        norm = float(p.grad.double().norm())
-        if abs(norm - summ[1]) > 5e-3 * summ[1] + 1e-7:
-            bad.append((str(name), norm, float(summ[1])))
+    bad = check_param_grads(dict(m.named_parameters()), g)     # norm AND 64 strided values per parameter
     assert not bad, bad[:8]
 
 
@@ -299,14 +282,5 @@ def test_benchmarked_training_regime_gradients_match_reference(golden_dir, cuda_
     for key, got in (("loss_mel", losses["loss_mel"][0]), ("loss_ctc", losses["loss_ctc"][0]), ("loss_bin", bin_loss),
                      ("total", total)):
         assert abs(float(got) - float(g[key])) < 1e-3 * abs(float(g[key])), (key, float(got), float(g[key]))
-    params = dict(model.named_parameters())
-    bad = []
-    for name, summ in zip(g["grad_names"], g["grad_sums"]):
-        p = params[str(name)]
-        if p.grad is None:
-            bad.append((str(name), "no grad"))
-            continue
-        norm = float(p.grad.double().norm())
-        if abs(norm - summ[1]) > 5e-3 * summ[1] + 1e-7:
-            bad.append((str(name), norm, float(summ[1])))
+    bad = check_param_grads(dict(model.named_parameters()), g)     # norm AND 64 strided values per parameter
     assert not bad, bad[:8]

@@ -51,3 +51,48 @@ def test_trainstep_gradients_equal_plain_autograd(cuda_lib):
         assert not bad, bad[:6]
     finally:
         ops.set_direct_grad_accumulation(False)
+
+
+def _lens_variant(batch, seed):
+    """Same padded shape, different (valid) lengths: what changes from replay to replay in a captured step."""
+    g = torch.Generator().manual_seed(seed)
+    b = {k: v.clone() for k, v in batch.items()}
+    B, _, T1 = b["mel"].shape
+    T2 = b["text"].shape[1]
+    il = torch.sort(torch.randint(T2 // 2, T2 + 1, (B,), generator=g), descending=True)[0]
+    il[0] = T2
+    ol = torch.maximum(torch.randint(T1 // 2, T1 + 1, (B,), generator=g), il)
+    ol[int(torch.randint(0, B, (1,), generator=g))] = T1
+    for i in range(B):
+        b["mel"][i, :, ol[i]:] = 0
+        b["text"][i, il[i]:] = 0
+        pr = synth.beta_binomial_prior(int(il[i]), int(ol[i]))
+        b["attn_prior"][i] = 0
+        b["attn_prior"][i, :ol[i], :il[i]] = torch.from_numpy(pr)
+    b["in_lens"], b["out_lens"] = il, ol
+    return b
+
+
+def test_graph_replayed_step_equals_eager_step(cuda_lib):
+    """The benchmarked executable: TrainStep captured as ONE CUDA graph (forward, losses, backward, clip, RAdam) against
+    the same TrainStep run eagerly, over 3 steps whose lengths change from step to step: loss, the flat gradient buffer
+    and the parameters after the fused RAdam update."""
+    base = synth.synth_batch(8, 320, 60, seed=777)
+    batches = [{k: v.cuda() for k, v in _lens_variant(base, s).items()} for s in (1, 2, 3)]
+    m_e, m_g = _model(), _model()         # eval mode: no dropout, no spectral-norm power iteration -> deterministic
+    eager = TrainStep(m_e, configs.LOSS_WEIGHTS, bf16=True, capturable=True)
+    graph = TrainStep(m_g, configs.LOSS_WEIGHTS, bf16=True, capturable=True)
+    # capture() warms up with 3 eager steps on its example batch: give the eager twin the same history
+    for _ in range(3):
+        eager._eager_step(batches[0])
+    graph.capture(batches[0])
+    assert graph.graph is not None and graph.launches_per_replay > 100
+    for i, b in enumerate(batches):
+        le = float(eager.step(b))
+        lg = float(graph.step(b))
+        assert abs(le - lg) < 1e-4 * abs(le), (i, le, lg)
+        ge, gg = eager.optimizer.grad, graph.optimizer.grad
+        assert float((ge - gg).norm() / ge.norm()) < 1e-4, i
+        pe, pg = eager.optimizer.flat, graph.optimizer.flat
+        assert float((pe - pg).norm() / pe.norm()) < 1e-6, i
+        assert int(eager.optimizer.step_dev) == int(graph.optimizer.step_dev) == 4 + i
