@@ -12,7 +12,10 @@
  *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
  *   - all launches are asynchronous on `stream`; return value 0 = ok, >0 = cudaError_t of the failing
  *     runtime call, <0 = RADTTS_ERR_* below;  no exceptions, no exit();
- *   - re-entrant; the only global state is cached cudaFuncSetAttribute / driver entry points.
+ *   - process-global state the library keeps: cached cudaFuncSetAttribute / driver entry points, a launch counter, ONE
+ *     internal side stream + two events per device (res_skip back-fill fork/join of the flow step, captured like any
+ *     other fork when the caller's stream is capturing), and a cache of TMA tensor maps keyed by (pointer, shape).
+ *     Calls on different streams are safe; two threads calling flow-step entry points concurrently are not.
  */
 #ifndef RADTTS_B200_H_
 #define RADTTS_B200_H_
@@ -218,6 +221,24 @@ typedef struct radtts_flow_wn_grads {
 RADTTS_API int radtts_flow_weight_norm_backward(const radtts_flow_dims* dims, const radtts_flow_weights* w,
                                                 const radtts_flow_grad_buffers* g, const radtts_flow_wn_grads* out,
                                                 int accumulate, void* stream);
+
+/* LU-parameterised 1x1-conv weights of a stack of n_flows flows (Invertible1x1ConvLUS, reference common.py:407-428),
+ * batched over the flows:  W_k = P_k (tril(lower_k,-1) + diag(lower_diag_k)) (triu(upper_k,1) + diag(upper_diag_k)),
+ * log_det_k = sum log|upper_diag_k|.  Arrays suffixed _host are HOST arrays of n_flows entries (device pointers / ints);
+ * n_host[k] = channel count C_k <= 256; every matrix is dense row-major (C_k, C_k) float32; tmp_k is a (C_k, C_k) scratch.
+ * backward (what autograd derives): g_w_k = dL/dW_k with row stride g_w_ld_host[k], g_log_det_k a
+ * device scalar or NULL -> g_lower_k (strictly lower, zeros elsewhere), g_upper_k (strictly upper), g_upper_diag_k;
+ * all OVERWRITTEN.  n_flows <= 32 (compose) / 16 (backward). */
+RADTTS_API int radtts_lus_compose(int n_flows, const int* n_host, const float* const* lower_host,
+                                  const float* const* upper_host, const float* const* upper_diag_host,
+                                  const float* const* lower_diag_host, const float* const* p_host,
+                                  float* const* tmp_host, float* const* w_host, float* const* log_det_host, void* stream);
+RADTTS_API int radtts_lus_backward(int n_flows, const int* n_host, const float* const* lower_host,
+                                   const float* const* upper_host, const float* const* upper_diag_host,
+                                   const float* const* lower_diag_host, const float* const* p_host,
+                                   const float* const* g_w_host, const int* g_w_ld_host,
+                                   const float* const* g_log_det_host, float* const* tmp_host, float* const* g_lower_host,
+                                   float* const* g_upper_host, float* const* g_upper_diag_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Kernel 3 -- ConvAttention core: pairwise L2 distance + log-softmax over text + log prior + masked softmax.

@@ -237,12 +237,15 @@ def _v_and_g(conv):
     return conv.weight, None
 
 
-def _flow_weight_list(flow, inverse):
+def _flow_weight_list(flow, inverse, w_inv=None):
     """Flat list of fp32 weight tensors in the order FlowWeights expects (3 + 4 n_layers + 2 entries: weight_v where a
-    conv is weight-normed), followed by the 1 + 2 n_layers weight_g tensors (None where it is not)."""
+    conv is weight-normed), followed by the 1 + 2 n_layers weight_g tensors (None where it is not).  w_inv: the 1x1
+    matrix when the caller has already composed it (lus_compose_stack)."""
     wn = flow.affine_tfn.affine_param_predictor
     inv = flow.invtbl_conv
-    if hasattr(inv, "lower"):
+    if w_inv is not None:
+        pass
+    elif hasattr(inv, "lower"):
         w_inv = inv.inverse_weight() if inverse else inv.weight()
     else:
         w_inv = inv.inverse_weight() if inverse else inv.conv.weight.squeeze(-1)
@@ -477,6 +480,80 @@ class _FlowStackFn(torch.autograd.Function):
         return ops_backward.flow_stack_backward(ctx.saved, g_zout, g_log_s)
 
 
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+class _LUSStackFn(torch.autograd.Function):
+    """W_k = P_k L_k U_k and log|det W_k| for ALL flows of a stack (Invertible1x1ConvLUS, reference common.py:407-428)
+    in three launches, with the closed-form backward in two (csrc/lus.cu) -- instead of ~12 + ~30 tiny torch kernels
+    per flow.  Inputs: (lower, upper, upper_diag) x n then the buffers (p, lower_diag) x n; outputs W x n, log_det x n."""
+
+    @staticmethod
+    def forward(ctx, n, *ts):
+        lower, upper, ud = ts[0:3 * n:3], ts[1:3 * n:3], ts[2:3 * n:3]
+        p, ldiag = ts[3 * n::2], ts[3 * n + 1::2]
+        dev = lower[0].device
+        _lib.require_cuda(*ts)
+        cs = [int(t.shape[0]) for t in lower]
+        keep = [[t.detach().float().contiguous() for t in grp] for grp in (lower, upper, ud, ldiag, p)]
+        tmp = [torch.empty((c, c), dtype=torch.float32, device=dev) for c in cs]
+        w = [torch.empty((c, c), dtype=torch.float32, device=dev) for c in cs]
+        ld = torch.empty(n, dtype=torch.float32, device=dev)
+        lds = [ld[k] for k in range(n)]
+        _lib.check(_lib.lib().radtts_lus_compose(n, (ctypes.c_int * n)(*cs), _ptr_array(keep[0]), _ptr_array(keep[1]),
+                                                 _ptr_array(keep[2]), _ptr_array(keep[3]), _ptr_array(keep[4]),
+                                                 _ptr_array(tmp), _ptr_array(w), _ptr_array(lds),
+                                                 _lib.stream_of(lower[0])), "radtts_lus_compose")
+        ctx.n, ctx.cs = n, cs
+        ctx.save_for_backward(*[t for grp in keep for t in grp])
+        return tuple(w) + tuple(lds)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        n, cs = ctx.n, ctx.cs
+        sv = ctx.saved_tensors
+        lower, upper, ud, ldiag, p = (sv[i * n:(i + 1) * n] for i in range(5))
+        dev = lower[0].device
+        g_w, g_ld = list(gs[:n]), list(gs[n:])
+        zeros = None
+        g_w_c, g_w_ld = [], []
+        for k in range(n):
+            g = g_w[k]
+            if g is None:
+                g = torch.zeros((cs[k], cs[k]), dtype=torch.float32, device=dev)
+            elif g.dtype != torch.float32 or g.stride(1) != 1:
+                g = g.float().contiguous()
+            g_w_c.append(g)
+            g_w_ld.append(int(g.stride(0)))
+        g_ld_c = [None if g is None else g.float().contiguous() for g in g_ld]
+        tmp = [torch.empty((c, c), dtype=torch.float32, device=dev) for c in cs]
+        gl = [torch.empty((c, c), dtype=torch.float32, device=dev) for c in cs]
+        gu = [torch.empty((c, c), dtype=torch.float32, device=dev) for c in cs]
+        gd = [torch.empty(c, dtype=torch.float32, device=dev) for c in cs]
+        _lib.check(_lib.lib().radtts_lus_backward(n, (ctypes.c_int * n)(*cs), _ptr_array(lower), _ptr_array(upper),
+                                                  _ptr_array(ud), _ptr_array(ldiag), _ptr_array(p), _ptr_array(g_w_c),
+                                                  (ctypes.c_int * n)(*g_w_ld), _ptr_array(g_ld_c), _ptr_array(tmp),
+                                                  _ptr_array(gl), _ptr_array(gu), _ptr_array(gd),
+                                                  _lib.stream_of(lower[0])), "radtts_lus_backward")
+        out = [None]
+        for k in range(n):
+            out += [gl[k], gu[k], gd[k]]
+        return tuple(out) + (None,) * (2 * n)
+
+
+def lus_compose_stack(convs):
+    """[Invertible1x1ConvLUS] -> ([W_k], [log_det_k]) with autograd links to lower / upper / upper_diag."""
+    n = len(convs)
+    ts = []
+    for c in convs:
+        ts += [c.lower, c.upper, c.upper_diag]
+    for c in convs:
+        ts += [c.p, c.lower_diag]
+    out = _LUSStackFn.apply(n, *ts)
+    return list(out[:n]), list(out[n:])
+
+
 def ctx_ld_of(n_ctx):
     return (n_ctx + 63) // 64 * 64
 
@@ -507,9 +584,14 @@ def flow_stack_packed(flows, zin, ctx_packed, plan, z_ld, actives, inverse=False
         blobs = [_cached_blob(f, d, prec, inverse, zin.device) for f, d in zip(flows, dims_list)]
         out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, 0, None, *blobs)
     else:
+        # training direction with LU-parameterised 1x1 convs: W = P L U and log|det| of the whole stack in one batched
+        # Function (csrc/lus.cu) instead of ~40 tiny torch kernels per flow
+        lus_w = lus_ld = None
+        if not inverse and len(flows) <= 16 and zin.is_cuda and all(hasattr(f.invtbl_conv, "lower") for f in flows):
+            lus_w, lus_ld = lus_compose_stack([f.invtbl_conv for f in flows])
         ws = []
-        for f in flows:
-            ws += _flow_weight_list(f, inverse)
+        for i, f in enumerate(flows):
+            ws += _flow_weight_list(f, inverse, None if lus_w is None else lus_w[i])
         n_per = len(ws) // len(flows)
         # gradient sinks: with direct accumulation on, the weight-norm backward kernel adds grad_v / grad_g straight
         # into the parameters' existing .grad (e.g. views of the optimizer's flat buffer) instead of handing 144 tensors
@@ -519,6 +601,8 @@ def flow_stack_packed(flows, zin, ctx_packed, plan, z_ld, actives, inverse=False
     if inverse:
         return out
     zout, log_s = out[0], list(out[1:])
+    if torch.is_grad_enabled() and lus_ld is not None:
+        return zout, lus_ld, log_s
     log_dets = []
     for f in flows:
         inv = f.invtbl_conv
