@@ -207,6 +207,15 @@ RADTTS_API int radtts_flowstep_backward(const radtts_flow_dims* dims, const void
                                         int Tmax, const radtts_flow_buffers* fwd, const radtts_flow_grad_buffers* g,
                                         int accumulate_ctx, int precision, void* stream);
 
+/* The same with an auxiliary stream (bf16 only; NULL = none): the memory-bound helpers that nothing on the NEXT flow's
+ * dgrad chain depends on (fp32 1x1-conv weight gradient, bias column sums, `end` de-interleave) are enqueued on
+ * aux_stream, ordered after the dgrad chain / the batched wgrad launch by events.  The caller must (i) not reuse the
+ * scratch or gradient buffers of this call before aux_stream has finished with them and (ii) join aux_stream before
+ * anything reads the gradients. */
+RADTTS_API int radtts_flowstep_backward_ex(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
+                                           int Tmax, const radtts_flow_buffers* fwd, const radtts_flow_grad_buffers* g,
+                                           int accumulate_ctx, int precision, void* stream, void* aux_stream);
+
 /* Weight-norm backward for the convs of one flow (what autograd derives for torch._weight_norm, reference
  * common.py:540-556): from the effective-weight gradients radtts_flowstep_backward wrote (g_w_start, TAP-MAJOR
  * g_w_in, g_w_rs) to the gradients of weight_v (reference layout) and weight_g:

@@ -112,7 +112,7 @@ __global__ void end_grad_unpack_kernel(const float* __restrict__ tmp, int ldt, i
 template <typename T>
 static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const PlanView& pv,
                          const radtts_flow_buffers& f, const radtts_flow_grad_buffers& g, int accumulate_ctx,
-                         cudaStream_t st) {
+                         cudaStream_t st, cudaStream_t aux) {
   const int prec = sizeof(T) == 4 ? RADTTS_PREC_FP32 : RADTTS_PREC_BF16;
   FlowLayout L = flow_layout(d, prec, 1);
   const int h = d.c_active / 2, nc = d.n_ch, k = d.ksize, nl = d.n_layers;
@@ -187,6 +187,23 @@ static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const P
 
   // 6. weight gradients -------------------------------------------------------------------------------
   // bf16: every problem of this flow goes into ONE batched tcgen05 launch; fp32: SIMT launches with atomics.
+  // With an auxiliary stream (bf16 only) the memory-bound helpers -- the fp32 1x1-conv weight gradient, the bias
+  // column sums and the `end` de-interleave -- leave the caller's stream: nothing on the dgrad chain of the NEXT flow
+  // needs them, so they run underneath its tensor-bound GEMMs.  The caller joins `aux` before it reads any gradient.
+  SideStream* sev = nullptr;
+  cudaStream_t sa = st;
+  if (aux && aux != st && sizeof(T) == 2) {
+    sev = side_stream();
+    if (!sev) return RADTTS_ERR_UNSUPPORTED;
+    sa = aux;
+  }
+  float* tmp = g.scratch_f32;
+  const int ldt = nc + 1;
+  RB_CUDA(cudaMemsetAsync(tmp, 0, (size_t)d.z_ld * ldt * sizeof(float), st));
+  if (sev) {
+    RB_CUDA(cudaEventRecord(sev->fork[kSideForks - 1], st));
+    RB_CUDA(cudaStreamWaitEvent(sa, sev->fork[kSideForks - 1], 0));
+  }
   WgradBatch batch;
   batch.rows_alloc = rows;
   ColsumBatch<T> sums;
@@ -203,23 +220,20 @@ static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const P
   };
   // 1x1 conv: dW_full[c][j] = sum_r g_zmid[r][c] zin[r][j]   (fp32 always)
   {
-    RB_CUDA(cudaMemsetAsync(g.g_w_inv_full, 0, (size_t)d.z_ld * d.z_ld * sizeof(float), st));
+    RB_CUDA(cudaMemsetAsync(g.g_w_inv_full, 0, (size_t)d.z_ld * d.z_ld * sizeof(float), sa));
     if (d.z_ld == kInvMaxLd) {
-      RB_TRY(launch_invconv_wgrad(g.g_zmid, f.zin, pv.hdr(), rows, g.g_w_inv_full, st));
+      RB_TRY(launch_invconv_wgrad(g.g_zmid, f.zin, pv.hdr(), rows, g.g_w_inv_full, sa));
     } else {
       WgradProb p{g.g_zmid, d.z_ld, 0, d.z_ld, f.zin, d.z_ld, 0, d.z_ld, 0, g.g_w_inv_full, d.z_ld, 1};
-      RB_TRY((launch_wgrad_simt<float, float>(p, pv.hdr(), rows, st)));
+      RB_TRY((launch_wgrad_simt<float, float>(p, pv.hdr(), rows, sa)));
     }
   }
   // end: interleaved rows into scratch, the n_layers K-blocks of r accumulate; bias = column sums of g_params
-  float* tmp = g.scratch_f32;
-  const int ldt = nc + 1;
-  RB_CUDA(cudaMemsetAsync(tmp, 0, (size_t)d.z_ld * ldt * sizeof(float), st));
   for (int l = 0; l < nl; ++l) {
     WgradProb p{gparams, L.end_kpad, 0, d.z_ld, r, nl * nc, l * nc, nc, 0, tmp, ldt, 1};
     RB_TRY(wgrad(p, true));
   }
-  RB_TRY(sums.add(gparams, L.end_kpad, 0, d.z_ld, 0, 0, tmp + nc, ldt, false, st));
+  RB_TRY(sums.add(gparams, L.end_kpad, 0, d.z_ld, 0, 0, tmp + nc, ldt, false, sa));
   for (int i = 0; i < nl; ++i) {
     const T* gui = gu + (size_t)i * rows * nc;
     const T* gvi = gv + (size_t)i * rows * nc;
@@ -229,7 +243,7 @@ static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const P
       WgradProb p{gui, nc, 0, nc, x + (size_t)(i + 1) * rows * nc, nc, 0, nc, 0, g.g_w_rs[i], nc, 1};
       RB_TRY(wgrad(p, false));
     }
-    RB_TRY(sums.add(gui, nc, 0, nc, 0, 0, g.g_b_rs[i], 1, true, st));
+    RB_TRY(sums.add(gui, nc, 0, nc, 0, 0, g.g_b_rs[i], 1, true, sa));
     // in_layer_i (tap-major output [t][n][c]): dW[t][n][c] = sum_r g_v_i[r][n] x_i[r + (t - half) d][c]
     if (kNeedZero) RB_CUDA(cudaMemsetAsync(g.g_w_in[i], 0, (size_t)nc * nc * k * sizeof(float), st));
     for (int t = 0; t < k; ++t) {
@@ -238,7 +252,7 @@ static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const P
       RB_TRY(wgrad(p, false));
     }
     // bias sits outside the partial-conv renormalisation: g_bias = sum_r g_v / ratio
-    RB_TRY(sums.add(gvi, nc, 0, nc, d.partial_padding, i, g.g_b_in[i], 1, true, st));
+    RB_TRY(sums.add(gvi, nc, 0, nc, d.partial_padding, i, g.g_b_in[i], 1, true, sa));
   }
   // start: the two K segments land directly in the reference layout [z0 (h) | ctx (n_ctx)]
   {
@@ -248,11 +262,15 @@ static int backward_impl(const radtts_flow_dims& d, const uint8_t* base, const P
     RB_TRY(wgrad(pc, false));
     WgradProb pz{gx0, nc, 0, nc, f.z0, 128, 0, h, 0, g.g_w_start, ldo, 1};
     RB_TRY(wgrad(pz, false));
-    RB_TRY(sums.add(gx0, nc, 0, nc, 0, 0, g.g_b_start, 1, true, st));
+    RB_TRY(sums.add(gx0, nc, 0, nc, 0, 0, g.g_b_start, 1, true, sa));
   }
+  RB_TRY(sums.launch(meta, k, pv.hdr(), rows, sa));
   RB_TRY(batch.launch(pv.hdr(), st));
-  RB_TRY(sums.launch(meta, k, pv.hdr(), rows, st));
-  end_grad_unpack_kernel<<<grid_for((size_t)2 * h * ldt), 256, 0, st>>>(tmp, ldt, h, nc, g.g_w_end, g.g_b_end);
+  if (sev) {
+    RB_CUDA(cudaEventRecord(sev->fork[kSideForks - 2], st));
+    RB_CUDA(cudaStreamWaitEvent(sa, sev->fork[kSideForks - 2], 0));
+  }
+  end_grad_unpack_kernel<<<grid_for((size_t)2 * h * ldt), 256, 0, sa>>>(tmp, ldt, h, nc, g.g_w_end, g.g_b_end);
   RB_TRY(after_launch());
   return 0;
 }
@@ -326,9 +344,18 @@ __global__ void __launch_bounds__(256) wn_bwd_kernel(const WnBwdParams p) {
 
 using namespace rb;
 
+extern "C" int radtts_flowstep_backward_ex(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
+                                           int Tmax, const radtts_flow_buffers* fwd, const radtts_flow_grad_buffers* g,
+                                           int accumulate_ctx, int precision, void* stream, void* aux_stream);
 extern "C" int radtts_flowstep_backward(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
                                         int Tmax, const radtts_flow_buffers* fwd, const radtts_flow_grad_buffers* g,
                                         int accumulate_ctx, int precision, void* stream) {
+  return radtts_flowstep_backward_ex(dims, prepared, plan, B, Tmax, fwd, g, accumulate_ctx, precision, stream, nullptr);
+}
+
+extern "C" int radtts_flowstep_backward_ex(const radtts_flow_dims* dims, const void* prepared, const void* plan, int B,
+                                           int Tmax, const radtts_flow_buffers* fwd, const radtts_flow_grad_buffers* g,
+                                           int accumulate_ctx, int precision, void* stream, void* aux_stream) {
   RB_TRY(check_dims(dims));
   if (!prepared || !plan || !fwd || !g || B <= 0 || Tmax <= 0) return RADTTS_ERR_INVALID_ARG;
   if (!fwd->ctx || !fwd->zin || !fwd->zmid || !fwd->z0 || !fwd->x || !fwd->r || !fwd->params) return RADTTS_ERR_INVALID_ARG;
@@ -340,9 +367,10 @@ extern "C" int radtts_flowstep_backward(const radtts_flow_dims* dims, const void
   PlanView pv = make_plan_view(plan, B, Tmax);
   const uint8_t* base = reinterpret_cast<const uint8_t*>(prepared);
   if (precision == RADTTS_PREC_FP32)
-    return backward_impl<float>(*dims, base, pv, *fwd, *g, accumulate_ctx, (cudaStream_t)stream);
+    return backward_impl<float>(*dims, base, pv, *fwd, *g, accumulate_ctx, (cudaStream_t)stream, nullptr);
   if (precision == RADTTS_PREC_BF16)
-    return backward_impl<__nv_bfloat16>(*dims, base, pv, *fwd, *g, accumulate_ctx, (cudaStream_t)stream);
+    return backward_impl<__nv_bfloat16>(*dims, base, pv, *fwd, *g, accumulate_ctx, (cudaStream_t)stream,
+                                        (cudaStream_t)aux_stream);
   return RADTTS_ERR_INVALID_ARG;
 }
 

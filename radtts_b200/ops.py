@@ -434,6 +434,51 @@ def run_flowstep(dims, blob, plan, zin, ctx_packed, prec, inverse, lease, keep_p
     return bufs["zout"], (None if inverse else bufs["log_s"]), bufs, s
 
 
+_prep_streams = {}
+
+
+def prepare_flows_async(dims_list, ws, n_per_flow, prec, want_backward, device, order=None):
+    """radtts_flow_prepare of every flow of a stack on a side stream (forked from the current stream here, joined per
+    flow by the returned events): ([blob_i], [event_i])."""
+    side = _prep_streams.get(device.index)
+    if side is None:
+        side = _prep_streams[device.index] = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    blobs, events = [None] * len(dims_list), [None] * len(dims_list)
+    with torch.cuda.stream(side):
+        for i in (order if order is not None else range(len(dims_list))):
+            blobs[i] = prepare_flow(dims_list[i], ws[i * n_per_flow:(i + 1) * n_per_flow], prec, want_backward, device)
+            events[i] = torch.cuda.Event()
+            events[i].record(side)
+    return blobs, events
+
+
+class FlowPrep:
+    """Result of begin_flow_prep: the stack's weight tensors (autograd-linked), LUS log-dets and the prepared blobs."""
+    __slots__ = ("ws", "n_per", "lus_ld", "dims_list", "prec", "prepared")
+
+
+def begin_flow_prep(flows, z_ld, actives, prec=None):
+    """Training direction: composes the LU-parameterised 1x1 matrices (batched, autograd-linked) and starts the weight
+    preparation of ALL flows on a side stream.  Called at the very top of RADTTS.forward, it hides the preparation
+    underneath the text encoder / attention / context-LSTM stages; flow_stack_packed(prep=...) picks the result up."""
+    prec = current_precision() if prec is None else prec
+    dev = flows[0].invtbl_conv.parameters().__next__().device
+    fp = FlowPrep()
+    fp.dims_list = [_flow_dims(f, z_ld, c) for f, c in zip(flows, actives)]
+    fp.prec = prec
+    lus_w = fp.lus_ld = None
+    if len(flows) <= 16 and all(hasattr(f.invtbl_conv, "lower") for f in flows):
+        lus_w, fp.lus_ld = lus_compose_stack([f.invtbl_conv for f in flows])
+    ws = []
+    for i, f in enumerate(flows):
+        ws += _flow_weight_list(f, False, None if lus_w is None else lus_w[i])
+    fp.ws, fp.n_per = ws, len(ws) // len(flows)
+    with torch.no_grad():
+        fp.prepared = prepare_flows_async(fp.dims_list, ws, fp.n_per, prec, True, dev)
+    return fp
+
+
 class _FlowStackFn(torch.autograd.Function):
     """A run of consecutive decoder flows on packed rows (the whole 8-flow stack in RADTTS.forward, a single flow
     for FlowStep.forward).  Inputs: zin [rows][z_ld] fp32, ctx [rows][ctx_ld] act, then the weight tensors of
@@ -441,7 +486,7 @@ class _FlowStackFn(torch.autograd.Function):
     inside the library; the LUS composition of the 1x1 matrix is left to autograd).  Returns (zout, log_s_0, ...)."""
 
     @staticmethod
-    def forward(ctx, zin, ctx_packed, plan, dims_list, prec, inverse, n_per_flow, sinks, *ws):
+    def forward(ctx, zin, ctx_packed, plan, dims_list, prec, inverse, n_per_flow, sinks, prepared, *ws):
         need_bwd = (not inverse) and any(ctx.needs_input_grad)
         order = range(len(dims_list))
         if inverse:
@@ -449,10 +494,17 @@ class _FlowStackFn(torch.autograd.Function):
         z = zin.contiguous()
         log_s_all = [None] * len(dims_list)
         saved = [None] * len(dims_list)
+        main = torch.cuda.current_stream(z.device)
+        if n_per_flow != 0 and prepared is None and len(dims_list) > 1 and not os.environ.get("RADTTS_NO_PREP_STREAM"):
+            # weight norm + re-layout of flow i+1 (memory-bound) underneath the GEMMs of flow i (tensor-bound)
+            prepared = prepare_flows_async(dims_list, ws, n_per_flow, prec, need_bwd, z.device, list(order))
         for i in order:
             dims = dims_list[i]
             if n_per_flow == 0:
                 blob = ws[i]                                   # cached, already prepared (inference)
+            elif prepared is not None:
+                blob = prepared[0][i]
+                main.wait_event(prepared[1][i])
             else:
                 blob = prepare_flow(dims, ws[i * n_per_flow:(i + 1) * n_per_flow], prec, need_bwd, z.device)
             lease = _Lease()
@@ -574,19 +626,25 @@ def _cached_blob(flow, dims, prec, inverse, device):
     return blob
 
 
-def flow_stack_packed(flows, zin, ctx_packed, plan, z_ld, actives, inverse=False, prec=None):
-    """Runs `flows` (in order; reversed when inverse) on packed rows.  actives[i] = channels flow i transforms."""
+def flow_stack_packed(flows, zin, ctx_packed, plan, z_ld, actives, inverse=False, prec=None, prep=None):
+    """Runs `flows` (in order; reversed when inverse) on packed rows.  actives[i] = channels flow i transforms.
+    prep: a FlowPrep from begin_flow_prep (training direction, same flows / precision), or None."""
     prec = current_precision() if prec is None else prec
     dims_list = [_flow_dims(f, z_ld, c) for f, c in zip(flows, actives)]
+    lus_ld = None
     if not torch.is_grad_enabled():
         # inference: weights are frozen between calls -> the re-laid-out blobs are cached per flow (keyed on the
         # parameters' version counters), and neither weight norm nor W^-1 nor the re-layout run again
         blobs = [_cached_blob(f, d, prec, inverse, zin.device) for f, d in zip(flows, dims_list)]
-        out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, 0, None, *blobs)
+        out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, 0, None, None, *blobs)
+    elif prep is not None and not inverse and prep.prec == prec and len(prep.dims_list) == len(flows):
+        lus_ld = prep.lus_ld
+        sinks = [w if (_direct_grad and isinstance(w, torch.nn.Parameter)) else None for w in prep.ws] if _direct_grad else None
+        out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, prep.n_per, sinks, prep.prepared, *prep.ws)
     else:
         # training direction with LU-parameterised 1x1 convs: W = P L U and log|det| of the whole stack in one batched
         # Function (csrc/lus.cu) instead of ~40 tiny torch kernels per flow
-        lus_w = lus_ld = None
+        lus_w = None
         if not inverse and len(flows) <= 16 and zin.is_cuda and all(hasattr(f.invtbl_conv, "lower") for f in flows):
             lus_w, lus_ld = lus_compose_stack([f.invtbl_conv for f in flows])
         ws = []
@@ -597,11 +655,11 @@ def flow_stack_packed(flows, zin, ctx_packed, plan, z_ld, actives, inverse=False
         # into the parameters' existing .grad (e.g. views of the optimizer's flat buffer) instead of handing 144 tensors
         # to autograd's AccumulateGrad
         sinks = [w if (_direct_grad and isinstance(w, torch.nn.Parameter)) else None for w in ws] if _direct_grad else None
-        out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, n_per, sinks, *ws)
+        out = _FlowStackFn.apply(zin, ctx_packed, plan, dims_list, prec, inverse, n_per, sinks, None, *ws)
     if inverse:
         return out
     zout, log_s = out[0], list(out[1:])
-    if torch.is_grad_enabled() and lus_ld is not None:
+    if lus_ld is not None:
         return zout, lus_ld, log_s
     log_dets = []
     for f in flows:
@@ -644,6 +702,15 @@ def flow_step(flow, z, context, inverse=False, seq_lens=None):
     return unpack(zout, plan, C, 1, z_ld - C), log_det, unpack(log_s, plan, C // 2, 1, 0)
 
 
+def begin_decoder_prep(model):
+    """RADTTS.forward calls this first (training on CUDA): see begin_flow_prep."""
+    flows = list(model.flows)
+    if not flows or not all(_is_fused_flow(f) for f in flows):
+        return None
+    z_ld = model.n_mel_channels * model.n_group_size
+    return begin_flow_prep(flows, z_ld, _active_channels(model, z_ld))
+
+
 def _active_channels(model, z_ld):
     actives, c = [], z_ld
     for i in range(len(model.flows)):
@@ -653,7 +720,7 @@ def _active_channels(model, z_ld):
     return actives
 
 
-def decoder_forward(model, mel, context, out_lens):
+def decoder_forward(model, mel, context, out_lens, prep=None):
     """Training direction of the decoder loop (reference radtts.py:414,431-444) on packed frames: one pack,
     n_flows fused flow steps operating in place on the column suffix that is still active, one unpack."""
     _lib.require_cuda(mel, context)
@@ -665,7 +732,7 @@ def decoder_forward(model, mel, context, out_lens):
     n_ctx = context.shape[1]
     ctxp = pack(context, plan, 1, _act_dtype(prec), ctx_ld_of(n_ctx), 0, ctx_ld_of(n_ctx))
     actives = _active_channels(model, z_ld)
-    z, log_det_list, log_s = flow_stack_packed(list(model.flows), z, ctxp, plan, z_ld, actives, False, prec)
+    z, log_det_list, log_s = flow_stack_packed(list(model.flows), z, ctxp, plan, z_ld, actives, False, prec, prep)
     log_s_list = [unpack(ls, plan, c // 2, 1, 0) for ls, c in zip(log_s, actives)]
     z_mel = unpack(z, plan, z_ld, 1, 0)
     # the packed originals ride along (rows of gaps / beyond the lengths are exactly zero in all of them), so that the

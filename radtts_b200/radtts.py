@@ -213,6 +213,11 @@ class RADTTS(nn.Module):
     # ------------------------------------------------------------------------------------------------
     def forward(self, mel, speaker_ids, text, in_lens, out_lens, binarize_attention=False, attn_prior=None,
                 f0=None, energy_avg=None, voiced_mask=None, p_voiced=None):
+        prep = None
+        if "dec" in self.include_modules and mel.is_cuda and torch.is_grad_enabled():
+            # weight norm / LU composition / re-layout of all 8 flows start now, on a side stream, and finish underneath
+            # the text encoder, the attention and the context LSTM
+            prep = ops.begin_decoder_prep(self)
         speaker_vecs = self.encode_speaker(speaker_ids)
         text_enc, text_embeddings = self.encode_text(text, in_lens)
         log_s_list, log_det_W_list, z_mel = [], [], []
@@ -259,7 +264,7 @@ class RADTTS(nn.Module):
             else:
                 f0_aug = f0 * voiced_mask
             context_w_spkvec = self.preprocess_context(context, speaker_vecs, out_lens, f0_aug, energy_avg)
-            z_mel, log_det_W_list, log_s_list = ops.decoder_forward(self, mel, context_w_spkvec, out_lens)
+            z_mel, log_det_W_list, log_s_list = ops.decoder_forward(self, mel, context_w_spkvec, out_lens, prep=prep)
 
         duration_model_outputs = None
         if "dpm" in self.include_modules:
