@@ -22,17 +22,19 @@ def make_inputs(sd, batch, seed=0):
     B, _, T1 = batch["mel"].shape
     T2 = batch["text"].shape[1]
     keys = sd["embedding.weight"][batch["text"]].transpose(1, 2).contiguous()            # (B, 512, T2)
-    text_enc = torch.from_numpy(rng.standard_normal((B, 512, T2), dtype=np.float32) * 0.3)
+    text_enc = torch.from_numpy(rng.standard_normal((B, 512, T2), dtype=np.float32) * 0.3).to(batch["mel"].device)
     spk = sd["speaker_embedding.weight"][batch["speaker_ids"]]                          # (B, 16)
     return keys, text_enc, spk
 
 
 def hot_path_step(sd, batch, keys, text_enc, spk, backward=True):
     """Returns (loss, valid_frames).  `sd` must hold leaf tensors with requires_grad for flows.* / attention.*."""
-    key_mask = ~(torch.arange(batch["text"].shape[1])[None, :] < batch["in_lens"][:, None])
+    dev = batch["mel"].device
+    key_mask = ~(torch.arange(batch["text"].shape[1], device=dev)[None, :] < batch["in_lens"][:, None])
     attn_soft, attn_logprob = oflow.conv_attention(sd, "attention.", batch["mel"], keys, key_mask, batch["attn_prior"])
-    hard = torch.from_numpy(omas.binarize(attn_soft.detach().numpy(), batch["in_lens"].numpy(),
-                                          batch["out_lens"].numpy(), is_prob=True))
+    # the reference's round trip (radtts.py:326-334): D2H of attn_soft, serial host-side MAS, H2D of the hard map
+    hard = torch.from_numpy(omas.binarize(attn_soft.detach().float().cpu().numpy(), batch["in_lens"].cpu().numpy(),
+                                          batch["out_lens"].cpu().numpy(), is_prob=True)).to(dev)
     context = oflow.attention_context(text_enc, hard)                                  # consumer of the hard map
     ctx = oflow.squeeze_time(context, 2)
     ctx = torch.cat((ctx, spk[:, :, None].expand(-1, -1, ctx.shape[2])), 1)            # (B, 1040, T')

@@ -184,20 +184,30 @@ class ConvLSTMLinear(nn.Module):
             x = self.dropout(F.relu(conv(x)))
         return x
 
+    def _convs_masked(self, x, mask):
+        """All utterances at once: the reference crops every utterance to its length and runs the (zero-padded) conv
+        stack on it alone (common.py:246-255).  Zeroing the input beyond each length in front of every conv is the same
+        arithmetic on the valid frames -- no Python loop over the batch, no `int(lens[b])` host read."""
+        for conv in self.convolutions:
+            x = self.dropout(F.relu(conv(x * mask)))
+        return x * mask
+
     def forward(self, context, lens):
-        if context.shape[0] > 1:
-            # per-utterance crop so that zero padding never enters the receptive field (common.py:246-255)
-            pieces = [self._convs(context[b:b + 1, :, :int(lens[b])])[0].transpose(0, 1)
-                      for b in range(context.shape[0])]
-            context = nn.utils.rnn.pad_sequence(pieces, batch_first=True).transpose(1, 2)
+        """context (B, C, T), lens (B,) or None (every utterance has T frames).  Output (B, out_dim, T) -- the reference
+        returns max(lens) frames for B > 1, which equals T for every batch its DataCollate builds."""
+        B, _, T = context.shape
+        if B > 1 and lens is not None:
+            mask = get_mask_from_lengths(lens.to(context.device), T)[:, None].to(context.dtype)
+            context = self._convs_masked(context, mask)
         else:
             context = self._convs(context)
         if self.lstm_type != "":
             x = context.transpose(1, 2)
-            if lens is not None:
-                packed = nn.utils.rnn.pack_padded_sequence(x, lens.long().cpu(), batch_first=True,
-                                                           enforce_sorted=False)
-                x = nn.utils.rnn.pad_packed_sequence(self.bilstm(packed)[0], batch_first=True)[0]
+            full = lens if lens is not None else torch.full((B,), T, dtype=torch.int64, device=context.device)
+            if lstm_ops.supported(self.bilstm, x):
+                x = lstm_ops.bilstm(self.bilstm, x, full)
+            elif lens is not None:
+                x = _cudnn_packed_lstm(self.bilstm, x, lens)
             else:
                 x = self.bilstm(x)[0]
             context = x.transpose(1, 2)
@@ -206,14 +216,20 @@ class ConvLSTMLinear(nn.Module):
         return context
 
 
+def _cudnn_packed_lstm(lstm, x, lens):
+    """The reference's packed-sequence cuDNN call (common.py:257-275), for LSTMs the persistent kernel does not cover
+    (unidirectional, hidden size > 592).  Costs a device->host read of the lengths."""
+    packed = nn.utils.rnn.pack_padded_sequence(x, lens.long().cpu(), batch_first=True, enforce_sorted=False)
+    return nn.utils.rnn.pad_packed_sequence(lstm(packed)[0], batch_first=True, total_length=x.shape[1])[0]
+
+
 def run_bilstm(lstm, x, lens):
-    """pad_packed(lstm(pack_padded(x, lens))) for a batch-first BiLSTM: the persistent CUDA recurrence when the shape
-    fits (csrc/lstm.cu), otherwise the cuDNN packed-sequence path the reference uses."""
+    """pad_packed(lstm(pack_padded(x, lens))) for a batch-first BiLSTM on the persistent CUDA recurrence (csrc/lstm.cu;
+    batches larger than its 32-utterance limit run in chunks -- utterances are independent).  Only a shape the kernel
+    cannot take at all (hidden size > 592, CPU tensors) goes to the cuDNN packed-sequence path the reference uses."""
     if lstm_ops.supported(lstm, x):
         return lstm_ops.bilstm(lstm, x, lens)
-    packed = nn.utils.rnn.pack_padded_sequence(x, lens.long().cpu(), batch_first=True, enforce_sorted=False)
-    out, _ = nn.utils.rnn.pad_packed_sequence(lstm(packed)[0], batch_first=True, total_length=x.shape[1])
-    return out
+    return _cudnn_packed_lstm(lstm, x, lens)
 
 
 class Encoder(nn.Module):

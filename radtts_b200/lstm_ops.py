@@ -29,7 +29,7 @@ class _rnn_matmul_precision:
 
 def supported(lstm, x):
     return (x.is_cuda and isinstance(lstm, torch.nn.LSTM) and lstm.bidirectional and lstm.num_layers == 1
-            and x.shape[0] <= MAX_B and lstm.hidden_size <= MAX_H and lstm.proj_size == 0)
+            and lstm.hidden_size <= MAX_H and lstm.proj_size == 0)
 
 
 def _effective_weights(lstm):
@@ -111,6 +111,13 @@ def bilstm(lstm, x, lens):
     """x (B, T, In) batch-first, lens (B,) -> (B, T, 2H) with zeros beyond each length."""
     w_ih, w_hh, bias = _effective_weights(lstm)
     lens32 = lens.to(device=x.device, dtype=torch.int32).contiguous()
-    x_tm = x.transpose(0, 1).contiguous()
-    h = _BiLSTMFn.apply(x_tm, lens32, w_ih, w_hh, bias)
-    return h.transpose(0, 1)
+    if x.shape[0] <= MAX_B:
+        x_tm = x.transpose(0, 1).contiguous()
+        return _BiLSTMFn.apply(x_tm, lens32, w_ih, w_hh, bias).transpose(0, 1)
+    # the kernel keeps <= 32 utterances per launch (one MMA N-tile): larger batches run in chunks, utterances being
+    # independent (weight gradients accumulate across the chunks through autograd)
+    outs = []
+    for lo in range(0, x.shape[0], MAX_B):
+        x_tm = x[lo:lo + MAX_B].transpose(0, 1).contiguous()
+        outs.append(_BiLSTMFn.apply(x_tm, lens32[lo:lo + MAX_B].contiguous(), w_ih, w_hh, bias).transpose(0, 1))
+    return torch.cat(outs, 0)

@@ -319,24 +319,29 @@ class RADTTS(nn.Module):
     def infer(self, speaker_id, text, sigma, sigma_dur=0.8, sigma_f0=0.8, sigma_energy=0.8,
               token_dur_scaling=1.0, token_duration_max=100, speaker_id_text=None, speaker_id_attributes=None,
               dur=None, f0=None, energy_avg=None, voiced_mask=None, f0_mean=0.0, f0_std=0.0, energy_mean=0.0,
-              energy_std=0.0):
+              energy_std=0.0, in_lens=None):
+        """reference radtts.py:541-684.  `in_lens` (B,) is an extension for BATCHED synthesis of padded text (the
+        reference's predictors cannot run with batch > 1): the text encoder and the duration
+        predictor then respect each utterance's length and padded tokens get duration 0.  None = reference behaviour."""
         batch_size, n_tokens = text.shape[0], text.shape[1]
         dev = text.device
         spk_vec = self.encode_speaker(speaker_id)
         spk_vec_text = spk_vec if speaker_id_text is None else self.encode_speaker(speaker_id_text)
         spk_vec_attributes = spk_vec if speaker_id_attributes is None else self.encode_speaker(
             speaker_id_attributes)
-        txt_enc, _ = self.encode_text(text, None)
+        txt_enc, _ = self.encode_text(text, in_lens)
 
         if dur is None:
             z_dur = _noise((batch_size, 1, n_tokens), dev) * sigma_dur
-            dur = self.dur_pred_layer.infer(z_dur, txt_enc, spk_vec_text)
+            dur = self.dur_pred_layer.infer(z_dur, txt_enc, spk_vec_text, lens=in_lens)
             if dur.shape[-1] < txt_enc.shape[-1]:
                 dur = nn.functional.pad(dur, (0, txt_enc.shape[-1] - dur.shape[2]), mode="replicate")
             dur = dur[:, 0].clamp(0, token_duration_max)
             if token_dur_scaling > 0:
                 dur = dur * token_dur_scaling
             dur = (dur + 0.5).floor().int()
+            if in_lens is not None:
+                dur = dur * get_mask_from_lengths(in_lens.to(dev), n_tokens).to(dur.dtype)
 
         out_lens = dur.sum(1).long().to(dev)
         max_n_frames = int(out_lens.max())
@@ -344,7 +349,8 @@ class RADTTS(nn.Module):
 
         if not self.is_attribute_unconditional():
             if voiced_mask is None and self.use_vpred_module:
-                logits = self.v_pred_module.infer(None, txt_enc_time_expanded, spk_vec_attributes)
+                logits = self.v_pred_module.infer(None, txt_enc_time_expanded, spk_vec_attributes,
+                                                  lens=out_lens if batch_size > 1 else None)
                 voiced_mask = (torch.sigmoid(logits[:, 0]) > 0.5).float()
             ap_txt = txt_enc_time_expanded
             if self.ap_use_voiced_embeddings:
@@ -356,6 +362,8 @@ class RADTTS(nn.Module):
             if f0 is None:
                 n_ch = 2 if self.use_first_order_features else 1
                 z_f0 = _noise((batch_size, n_ch, max_n_frames), dev) * sigma_f0
+                if batch_size > 1:      # batched extension: the padded region must look like the zero padding a
+                    z_f0 = z_f0 * get_mask_from_lengths(out_lens, max_n_frames)[:, None].to(z_f0.dtype)   # B=1 run sees
                 f0 = self.infer_f0(z_f0, ap_txt, spk_vec_attributes, voiced_mask, out_lens)[:, 0]
             if f0_mean > 0.0:
                 vb = voiced_mask.bool()
@@ -365,6 +373,8 @@ class RADTTS(nn.Module):
             if energy_avg is None:
                 n_ch = 2 if self.use_first_order_features else 1
                 z_e = _noise((batch_size, n_ch, max_n_frames), dev) * sigma_energy
+                if batch_size > 1:
+                    z_e = z_e * get_mask_from_lengths(out_lens, max_n_frames)[:, None].to(z_e.dtype)
                 energy_avg = self.infer_energy(z_e, ap_txt, spk_vec, out_lens)[:, 0]
             n0 = int(out_lens[0])
             if energy_avg.shape[1] < n0:  # reference radtts.py:629-637 (both padded by the energy deficit)

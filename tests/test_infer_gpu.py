@@ -94,3 +94,70 @@ def test_infer_with_attribute_predictors_matches_reference(gold, cuda_lib, monke
         txt_enc, _ = m.encode_text(text, None)
         d = m.dur_pred_layer.infer(torch.from_numpy(gold["bgap_z_dur"]).cuda(), txt_enc, spk_vec)
     assert torch.allclose(d.cpu(), torch.from_numpy(gold["bgap_dur_raw"]), rtol=1e-3, atol=1e-4)
+
+
+def test_batched_predictors_equal_per_utterance_runs(cuda_lib):
+    """ConvLSTMLinear (DAP) on a padded batch -- masked batched convs + the persistent LSTM kernel -- must
+    equal the reference's per-utterance crop-and-loop (common.py:246-297), i.e. B=1 runs of every cropped utterance."""
+    m = _model("bgap")
+    torch.manual_seed(11)
+    B, T = 5, 37
+    lens = torch.tensor([37, 30, 22, 9, 3], device="cuda")
+    txt = torch.randn(B, 512, T, device="cuda") * 0.5
+    spk = torch.randn(B, 16, device="cuda") * 0.3
+    for b in range(B):
+        txt[b, :, lens[b]:] = 0
+    ops.set_precision("fp32")
+    try:
+        with torch.no_grad():
+            for mod in (m.dur_pred_layer, m.v_pred_module):
+                batched = mod.infer(None, txt, spk, lens=lens)
+                assert batched.shape[0] == B and batched.shape[2] == T
+                for b in range(B):
+                    n = int(lens[b])
+                    single = mod.infer(None, txt[b:b + 1, :, :n], spk[b:b + 1], lens=None)
+                    assert torch.allclose(batched[b:b + 1, :, :n], single, rtol=1e-4, atol=1e-5), (type(mod).__name__, b)
+    finally:
+        ops.set_precision(None)
+
+
+def test_batched_infer_with_in_lens_equals_per_utterance_infer(cuda_lib, monkeypatch):
+    """End-to-end batched synthesis (the `in_lens` extension of RADTTS.infer; the reference cannot batch its predictors,
+    SURVEY Appendix A-5): config_ljs_bgap, voicing / F0 / energy predicted, 3 padded utterances at once == three B=1 calls
+    fed the same noise."""
+    m = _model("bgap")
+    rng = np.random.default_rng(3)
+    B, T2 = 3, 12
+    in_lens = torch.tensor([12, 9, 5], device="cuda")
+    text = torch.from_numpy(rng.integers(1, 185, (B, T2)).astype(np.int64)).cuda()
+    dur = torch.from_numpy(rng.integers(2, 7, (B, T2)).astype(np.int64)).cuda()
+    for b in range(B):
+        text[b, in_lens[b]:] = 0
+        dur[b, in_lens[b]:] = 0
+        dur[b, 0] += (4 - int(dur[b].sum()) % 4) % 4           # SURVEY Appendix A-6
+    bank = torch.randn(B, 160, int(dur.sum(1).max()), device="cuda")
+    state = {"b": None}
+
+    def noise(shape, device):
+        n, c, t = shape
+        src = bank if state["b"] is None else bank[state["b"]:state["b"] + 1]
+        assert src.shape[0] == n
+        return src[:, :c, :t].clone()
+
+    monkeypatch.setattr(rmod, "_noise", noise)
+    spk = torch.zeros(B, dtype=torch.long, device="cuda")
+    ops.set_precision("fp32")
+    try:
+        with torch.no_grad():
+            out = m.infer(spk, text, 0.8, dur=dur, in_lens=in_lens)
+            for b in range(B):
+                state["b"] = b
+                n = int(in_lens[b])
+                one = m.infer(spk[b:b + 1], text[b:b + 1, :n], 0.8, dur=dur[b:b + 1, :n])
+                t = int(dur[b].sum())
+                assert torch.equal(out["voiced_mask"][b, :t], one["voiced_mask"][0, :t]), b
+                for k, tol in (("f0", 2e-3), ("energy_avg", 1e-4), ("mel", 5e-3)):
+                    a, r = out[k][b][..., :t], one[k][0][..., :t]
+                    assert torch.allclose(a, r, rtol=2e-3, atol=tol), (k, b, float((a - r).abs().max()))
+    finally:
+        ops.set_precision(None)
