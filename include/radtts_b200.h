@@ -280,6 +280,24 @@ RADTTS_API int radtts_conv_prepare(const float* w, const float* bias, int c_out,
 RADTTS_API int radtts_conv_rows(const void* prepared, int c_out, int c_in_pad, int ksize, int dilation, int act,
                                 int partial, int mask_rows, const void* x, int ld_x, void* y, int ld_y, int y_col_off,
                                 const void* plan, int B, int Tmax, int precision, void* stream);
+/* Backward of radtts_conv_rows (what autograd derives for ConvNorm / PartialConv1d + activation, reference
+ * common.py:145-154, partialconv1d.py:35-71): from g_y (act [rows][ld_gy], gradient w.r.t. the layer OUTPUT; zeros on gap
+ * rows) and the saved forward input x / output y to
+ *   g_x   act [rows][ld_gx] (first c_in_pad columns written; may be NULL for the first layer of a stack),
+ *   g_w   float32 (c_out, c_in, ksize), the reference layout, OVERWRITTEN,
+ *   g_b   float32, round_up(c_out, 16) floats, OVERWRITTEN (may be NULL).
+ * prepared_t: the transposed weights (radtts_conv_prepare_backward).  g_pre: scratch act [rows][round_up(c_out, 64)].
+ * act / partial / mask_rows / dilation as in the forward call.  The dgrad is a row GEMM with the taps reversed, the weight
+ * gradient one tcgen05 problem per tap with K = packed rows, the bias gradient a streaming column sum. */
+RADTTS_API size_t radtts_conv_backward_prepared_bytes(int c_out, int c_in_pad, int ksize, int precision);
+RADTTS_API int radtts_conv_prepare_backward(const float* w, int c_out, int c_in, int c_in_pad, int ksize, int precision,
+                                            void* prepared_t, size_t prepared_bytes, void* stream);
+RADTTS_API int radtts_conv_rows_backward(const void* prepared_t, int c_out, int c_in, int c_in_pad, int ksize, int dilation,
+                                         int act, int partial, int mask_rows, const void* x, int ld_x, const void* y,
+                                         int ld_y, int y_col_off, const void* g_y, int ld_gy, void* g_pre, void* g_x,
+                                         int ld_gx, float* g_w, float* g_b, const void* plan, int B, int Tmax,
+                                         int precision, void* stream);
+
 /* Rational-quadratic spline coupling transform (reference splines.py:221-319 through
  * SplineTransformationLayer.forward, common.py:699-743), (B, C, T) float32 tensors:
  * x: coupling input (first C/2 channels pass through, last C/2 are transformed); params (B, C/2 * (2 n_bins + 1), T)
@@ -298,8 +316,15 @@ RADTTS_API int radtts_rqspline_backward(const float* x, const float* params, con
  * scaling 0 tanh, 1 exp, 2 sigmoid, 3 translate.  log_s (B, C/2, T) forward only, may be NULL. */
 RADTTS_API int radtts_affine_apply(const float* z, const float* params, int B, int C, int T, int scaling, int inverse,
                                    float* y, float* log_s, void* stream);
-/* y[b,:,t] = W x[b,:,t] for a small dense W (C <= 16): the plain Invertible1x1Conv of BGAP (common.py:431-472). */
+/* Backward of radtts_affine_apply in the forward direction (training the attribute flows): g_y (B, C, T) / g_log_s
+ * (B, C/2, T) may be NULL (zeros) -> g_z (B, C, T), g_params (B, C, T). */
+RADTTS_API int radtts_affine_backward(const float* z, const float* params, const float* g_y, const float* g_log_s, int B,
+                                      int C, int T, int scaling, float* g_z, float* g_params, void* stream);
+/* y[b,:,t] = W x[b,:,t] for a small dense W (C <= 16): the plain Invertible1x1Conv of BGAP (common.py:431-472), and its
+ * backward: g_x = W^T g_y, g_w (C, C) = sum over (b, t) of g_y x^T (OVERWRITTEN). */
 RADTTS_API int radtts_pointwise_conv_small(const float* x, const float* w, int B, int C, int T, float* y, void* stream);
+RADTTS_API int radtts_pointwise_conv_small_backward(const float* x, const float* w, const float* g_y, int B, int C, int T,
+                                                    float* g_x, float* g_w, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Hard-attention context: context = bmm(text_enc, attn_hard^T) of reference radtts.py:399 as a gather by

@@ -74,3 +74,42 @@ def rq_spline_forward_backward(x, w_tilde, v_tilde, g_y, g_lj):
     # w = softmax(w~)
     g_wt = w * (g_w - (g_w * w).sum(-1, keepdim=True))
     return y, log_j, g_x, g_wt, g_vt
+
+
+# Differentiable torch restatement of splines.py:221-319 without boolean-index gathers (torch.where instead): the autograd
+# side of tests/test_host_logic_cpu.py, which pins the closed-form gradients above (and, through them, the CUDA backward
+# kernel radtts_rqspline_backward).  TEST INFRASTRUCTURE ONLY.
+def rq_spline_autograd(x, w_tilde, v_tilde, inverse):
+    """splines.py:221-319 (unbounded piecewise-quadratic transform) without boolean-index gathers: evaluated for every
+    element on a clamped copy of x and selected with torch.where, so there is no host synchronisation and the
+    gradient of elements outside [0, 1) is exactly the identity's."""
+    eps = torch.finfo(x.dtype).eps
+    inside = (x >= 0) & (x < 1)
+    xc = torch.where(inside, x, torch.full_like(x, 0.5))
+    w = torch.softmax(w_tilde, dim=-1)
+    v = torch.exp(v_tilde - v_tilde.max(dim=-1, keepdim=True)[0]) + 1e-8
+    v = v / (((v[..., :-1] + v[..., 1:]) / 2) * w).sum(-1, keepdim=True)
+    wc = torch.cumsum(w, -1)
+    wc = torch.cat((wc[..., :-1], torch.ones_like(wc[..., -1:])), -1)
+    wc0 = torch.nn.functional.pad(wc, (1, 0))
+    cdf = torch.cumsum((v[..., 1:] + v[..., :-1]) / 2 * w, -1)
+    cdf = torch.cat((cdf[..., :-1], torch.ones_like(cdf[..., -1:])), -1)
+    cdf0 = torch.nn.functional.pad(cdf, (1, 0))
+    knots = cdf if inverse else wc
+    idx = torch.searchsorted(knots.detach(), xc.detach().unsqueeze(-1)).clamp(max=w.shape[-1] - 1)
+    take = lambda t, i: torch.gather(t, -1, i).squeeze(-1)
+    w_b, w_lo = take(w, idx), take(wc0, idx)
+    v_b, v_n = take(v, idx), take(v, idx + 1)
+    c_lo = take(cdf0, idx)
+    if not inverse:
+        alpha = (xc - w_lo) / w_b.clamp(min=eps)
+        out = alpha ** 2 / 2 * (v_n - v_b) * w_b + alpha * v_b * w_b + c_lo
+        log_j = torch.lerp(v_b, v_n, alpha).clamp(min=eps).log()
+        out = out.clamp(min=eps, max=1.0 - eps)
+        return torch.where(inside, out, x), torch.where(inside, log_j, torch.zeros_like(log_j))
+    qa = (v_n - v_b) * w_b / 2
+    qb = v_b * w_b
+    qc = c_lo - xc
+    alpha = (-qb + torch.sqrt(qb ** 2 - 4 * qa * qc)) / (2 * qa)
+    out = (alpha * w_b + w_lo).clamp(min=eps, max=1.0 - eps)
+    return torch.where(inside, out, x), None

@@ -41,82 +41,138 @@ __device__ __forceinline__ void stage_qk(const float* __restrict__ q, const floa
   }
 }
 
+// Forward.  A CTA stages the utterance's projected keys ONCE (ks[c][t2] channel-major + a table of |k|^2) and then walks
+// over 32-frame tiles of that utterance (grid.x CTAs per utterance share its tiles round-robin), so the 100 KB key stage is
+// amortised over many tiles.  Inside a tile a warp owns FOUR consecutive frames: every key value fetched from smem feeds
+// four FMAs (the one-frame version was bound by shared-memory loads: one LDS per FMA), and the squared distance is
+// expanded, |q - k|^2 = |q|^2 + |k|^2 - 2 q.k -- one FMA per (frame, key, channel) instead of a subtract and an FMA.
+// The prior row of each frame is fetched into registers BEFORE the channel loop, which hides its DRAM latency.
+constexpr int kFwdRows = 32;
+constexpr int kFwdThreads = 256;
+constexpr int kFwdFr = 4;
+
 template <int NJ>
-__global__ void __launch_bounds__(kAttThreads) convattn_fwd_kernel(const float* __restrict__ q_enc, const float* __restrict__ k_enc,
+__global__ void __launch_bounds__(kFwdThreads) convattn_fwd_kernel(const float* __restrict__ q_enc, const float* __restrict__ k_enc,
                                                                    const float* __restrict__ prior, const int64_t* __restrict__ key_lens,
                                                                    int C, int T1, int T2, float temp, float* __restrict__ attn,
                                                                    float* __restrict__ logprob, float* __restrict__ lse_out) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int T2p = NJ * 32;
-  float* ks = sm;
-  float* qs = sm + (size_t)C * T2p;
-  const int b = blockIdx.y, t1_0 = blockIdx.x * kAttRows;
-  stage_qk(q_enc + (size_t)b * C * T1, k_enc + (size_t)b * C * T2, C, T1, T2, T2p, t1_0, ks, qs);
+  float* ks = sm;                                   // [C][T2p]
+  float* qs = sm + (size_t)C * T2p;                 // [C][kFwdRows]
+  float* kn = qs + (size_t)C * kFwdRows;            // [T2p]
+  const int b = blockIdx.y;
+  const float* q = q_enc + (size_t)b * C * T1;
+  {
+    const float* k = k_enc + (size_t)b * C * T2;
+    for (int i = threadIdx.x; i < C * T2p; i += kFwdThreads) {
+      const int c = i / T2p, t2 = i - c * T2p;
+      ks[i] = t2 < T2 ? k[(size_t)c * T2 + t2] : 0.f;
+    }
+  }
   __syncthreads();
+  for (int t2 = threadIdx.x; t2 < T2p; t2 += kFwdThreads) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) { const float v = ks[(size_t)c * T2p + t2]; s = fmaf(v, v, s); }
+    kn[t2] = s;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int klen = key_lens ? (int)min((long long)key_lens[b], (long long)T2) : T2;
-  for (int rr = warp; rr < kAttRows; rr += kAttThreads / 32) {
-    const int t1 = t1_0 + rr;
-    if (t1 >= T1) break;
-    float d[NJ];
+  const int r0 = warp * kFwdFr;
+  const int n_tiles = (T1 + kFwdRows - 1) / kFwdRows;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int t1_0 = tile * kFwdRows;
+    __syncthreads();                                // previous tile's readers of qs are done (and kn is visible)
+    for (int i = threadIdx.x; i < C * kFwdRows; i += kFwdThreads) {
+      const int c = i / kFwdRows, r = i - c * kFwdRows;
+      qs[i] = (t1_0 + r) < T1 ? q[(size_t)c * T1 + t1_0 + r] : 0.f;
+    }
+    __syncthreads();
+    if (t1_0 + r0 >= T1) continue;
+    // prior rows of this warp's frames, in flight underneath the channel loop
+    float pr[kFwdFr][NJ];
+    if (prior) {
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) d[j] = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float qc = qs[c * kAttRows + rr];
-      const float* kr = ks + (size_t)c * T2p + lane;
+      for (int f = 0; f < kFwdFr; ++f) {
+        const int t1 = t1_0 + r0 + f;
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const float df = qc - kr[32 * j];
-        d[j] = fmaf(df, df, d[j]);
+        for (int j = 0; j < NJ; ++j) {
+          const int t2 = lane + 32 * j;
+          pr[f][j] = (t1 < T1 && t2 < T2) ? __ldg(prior + ((size_t)b * T1 + t1) * T2 + t2) : 0.f;
+        }
       }
     }
-    const size_t row_off = ((size_t)b * T1 + t1) * T2;
-    float m = -CUDART_INF_F;
+    float dot[kFwdFr][NJ];
+    float qn[kFwdFr];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      d[j] *= -temp;
-      if (lane + 32 * j < T2) m = fmaxf(m, d[j]);
+    for (int f = 0; f < kFwdFr; ++f) {
+      qn[f] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) dot[f][j] = 0.f;
     }
-    float a[NJ];
-    if (prior) {
-      m = warp_max(m);
-      float s = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float4 q4 = *reinterpret_cast<const float4*>(qs + (size_t)c * kFwdRows + r0);
+      const float qv[kFwdFr] = {q4.x, q4.y, q4.z, q4.w};
+      const float* kr = ks + (size_t)c * T2p + lane;
 #pragma unroll
-      for (int j = 0; j < NJ; ++j)
-        if (lane + 32 * j < T2) s += expf(d[j] - m);
-      s = warp_sum(s);
-      const float lse = m + logf(s);
-      if (lane == 0 && lse_out) lse_out[(size_t)b * T1 + t1] = lse;
+      for (int f = 0; f < kFwdFr; ++f) qn[f] = fmaf(qv[f], qv[f], qn[f]);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const float kv = kr[32 * j];
+#pragma unroll
+        for (int f = 0; f < kFwdFr; ++f) dot[f][j] = fmaf(qv[f], kv, dot[f][j]);
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < kFwdFr; ++f) {
+      const int t1 = t1_0 + r0 + f;
+      if (t1 >= T1) break;
+      const size_t row_off = ((size_t)b * T1 + t1) * T2;
+      float d[NJ];
+      float m = -CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        d[j] = -temp * fmaxf(fmaf(-2.f, dot[f][j], qn[f] + kn[lane + 32 * j]), 0.f);
+        if (lane + 32 * j < T2) m = fmaxf(m, d[j]);
+      }
+      if (prior) {
+        m = warp_max(m);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          if (lane + 32 * j < T2) s += expf(d[j] - m);
+        s = warp_sum(s);
+        const float lse = m + logf(s);
+        if (lane == 0 && lse_out) lse_out[(size_t)b * T1 + t1] = lse;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          d[j] = (lane + 32 * j < T2) ? (d[j] - lse) + logf(pr[f][j] + 1e-8f) : -CUDART_INF_F;
+      } else {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          if (lane + 32 * j >= T2) d[j] = -CUDART_INF_F;
+      }
+      float m2 = -CUDART_INF_F;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int t2 = lane + 32 * j;
-        a[j] = t2 < T2 ? (d[j] - lse) + logf(prior[row_off + t2] + 1e-8f) : -CUDART_INF_F;
+        if (t2 < T2) logprob[row_off + t2] = d[j];
+        if (t2 < klen) m2 = fmaxf(m2, d[j]);
       }
-    } else {
+      m2 = warp_max(m2);
+      float s2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) a[j] = (lane + 32 * j < T2) ? d[j] : -CUDART_INF_F;
-    }
-    float m2 = -CUDART_INF_F;
+      for (int j = 0; j < NJ; ++j) {
+        d[j] = (lane + 32 * j < klen) ? expf(d[j] - m2) : 0.f;
+        s2 += d[j];
+      }
+      s2 = warp_sum(s2);
+      const float inv = 1.f / s2;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int t2 = lane + 32 * j;
-      if (t2 < T2) logprob[row_off + t2] = a[j];
-      if (t2 < klen) m2 = fmaxf(m2, a[j]);
-    }
-    m2 = warp_max(m2);
-    float s2 = 0.f;
-    float e[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      e[j] = (lane + 32 * j < klen) ? expf(a[j] - m2) : 0.f;
-      s2 += e[j];
-    }
-    s2 = warp_sum(s2);
-    const float inv = 1.f / s2;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int t2 = lane + 32 * j;
-      if (t2 < T2) attn[row_off + t2] = e[j] * inv;
+      for (int j = 0; j < NJ; ++j) {
+        const int t2 = lane + 32 * j;
+        if (t2 < T2) attn[row_off + t2] = d[j] * inv;
+      }
     }
   }
 }
@@ -256,15 +312,21 @@ __global__ void __launch_bounds__(256) convattn_bwd_cols_kernel(const float* __r
 template <int NJ>
 static int launch_fwd(const float* q, const float* k, const float* prior, const int64_t* key_lens, int B, int C, int T1,
                       int T2, float temp, float* attn, float* logprob, float* lse, cudaStream_t st) {
-  const size_t smem = ((size_t)C * NJ * 32 + (size_t)C * kAttRows) * sizeof(float);
+  const size_t smem = ((size_t)C * NJ * 32 + (size_t)C * kFwdRows + (size_t)NJ * 32) * sizeof(float);
   if (smem > (size_t)kSmemBudget) return RADTTS_ERR_UNSUPPORTED;
   static size_t configured = 0;
   if (smem > configured) {
     RB_CUDA(cudaFuncSetAttribute(convattn_fwd_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  dim3 grid(ceil_div(T1, kAttRows), B);
-  convattn_fwd_kernel<NJ><<<grid, kAttThreads, smem, st>>>(q, k, prior, key_lens, C, T1, T2, temp, attn, logprob, lse);
+  // ~2 CTAs per SM in total; every CTA of an utterance stages its keys once and walks its share of the frame tiles
+  // sized to ONE resident wave (1 or 2 CTAs per SM, whatever the key stage leaves room for)
+  const int n_tiles = ceil_div(T1, kFwdRows);
+  const int per_sm = (2 * (smem + 1024) <= (size_t)233472) ? 2 : 1;
+  int per_utt = per_sm * kNumSMs / B;
+  per_utt = per_utt < 1 ? 1 : (per_utt > n_tiles ? n_tiles : per_utt);
+  dim3 grid(per_utt, B);
+  convattn_fwd_kernel<NJ><<<grid, kFwdThreads, smem, st>>>(q, k, prior, key_lens, C, T1, T2, temp, attn, logprob, lse);
   return after_launch();
 }
 template <int NJ>

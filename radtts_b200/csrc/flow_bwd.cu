@@ -9,6 +9,7 @@
 //   6. weight gradients: wgrad GEMMs (K = packed rows) + bias column sums
 #include <cuda_bf16.h>
 
+#define RB_WGRAD_TC_DEFINE
 #include "flow_common.cuh"
 #include "invconv.cuh"
 #include "wgrad.cuh"

@@ -192,6 +192,65 @@ __global__ void __launch_bounds__(256) affine_apply_kernel(const float* __restri
   else { y[i1] = s * z[i1] + tr; if (log_s) log_s[base / 2 + (size_t)c * T + t] = ls; }
 }
 
+// Backward of the forward-direction affine coupling (what autograd derives for common.py:782-784,821-832):
+//   y1 = s z1 + b, log_s = log s, s = f(x)  ->  g_z0 = g_y0, g_z1 = s g_y1, g_b = g_y1, g_x = (g_y1 z1 + g_log_s / s) ds/dx
+__global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict__ z, const float* __restrict__ params,
+                                                         const float* __restrict__ g_y, const float* __restrict__ g_log_s,
+                                                         int h, int T, int scaling, float* __restrict__ g_z,
+                                                         float* __restrict__ g_params) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const size_t base = (size_t)b * 2 * h * T;
+  const size_t i0 = base + (size_t)c * T + t, i1 = base + (size_t)(h + c) * T + t;
+  const float gy0 = g_y ? g_y[i0] : 0.f, gy1 = g_y ? g_y[i1] : 0.f;
+  const float gl = g_log_s ? g_log_s[base / 2 + (size_t)c * T + t] : 0.f;
+  const float x = params[i0];
+  float s, ds, dls;
+  if (scaling == 0) { const float th = tanhf(x); s = (th + 1.f) + 1e-6f; ds = 1.f - th * th; dls = ds / s; }
+  else if (scaling == 1) { s = expf(x); ds = s; dls = 1.f; }
+  else if (scaling == 2) { const float sg = 1.f / (1.f + expf(-(x + 10.f))); s = sg + 1e-6f; ds = sg * (1.f - sg); dls = ds / s; }
+  else { s = 1.f; ds = 0.f; dls = 0.f; }
+  g_z[i0] = gy0;
+  g_z[i1] = s * gy1;
+  g_params[i0] = gy1 * z[i1] * ds + gl * dls;
+  g_params[i1] = gy1;
+}
+
+// Backward of the small dense 1x1 conv y[b,:,t] = W x[b,:,t] (C <= 16):  g_x = W^T g_y;  g_W[c][j] = sum_{b,t} g_y[c] x[j]
+__global__ void __launch_bounds__(256) pointwise_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                  const float* __restrict__ g_y, int C, int T,
+                                                                  float* __restrict__ g_x, float* __restrict__ g_w) {
+  __shared__ float ws[16 * 16];
+  __shared__ float acc_s[16 * 16];
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) { ws[i] = w[i]; acc_s[i] = 0.f; }
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  float xv[16], gv[16];
+  const bool ok = t < T;
+  for (int j = 0; j < C; ++j) {
+    xv[j] = ok ? x[((size_t)b * C + j) * T + t] : 0.f;
+    gv[j] = ok ? g_y[((size_t)b * C + j) * T + t] : 0.f;
+  }
+  if (ok) {
+    for (int j = 0; j < C; ++j) {
+      float a = 0.f;
+      for (int c = 0; c < C; ++c) a = fmaf(ws[c * C + j], gv[c], a);
+      g_x[((size_t)b * C + j) * T + t] = a;
+    }
+  }
+  for (int c = 0; c < C; ++c)
+    for (int j = 0; j < C; ++j) {
+      float v = gv[c] * xv[j];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&acc_s[c * C + j], v);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) atomicAdd(&g_w[i], acc_s[i]);
+}
+
 // out[b][c][t] = sum_j W[c][j] x[b][j][t], C <= 16
 __global__ void __launch_bounds__(256) pointwise_small_kernel(const float* __restrict__ x, const float* __restrict__ w, int C,
                                                               int T, float* __restrict__ y) {
@@ -249,5 +308,23 @@ extern "C" int radtts_rqspline_backward(const float* x, const float* params, con
   dim3 grid(ceil_div(T, 128), B);
   rqspline_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, params, g_y, g_log_s, B, C, C / 2, T, n_bins, left, right,
                                                              bottom, top, g_x, g_params);
+  return after_launch();
+}
+
+extern "C" int radtts_affine_backward(const float* z, const float* params, const float* g_y, const float* g_log_s, int B,
+                                      int C, int T, int scaling, float* g_z, float* g_params, void* stream) {
+  if (!z || !params || !g_z || !g_params || B <= 0 || C <= 0 || C % 2 || T <= 0) return RADTTS_ERR_INVALID_ARG;
+  dim3 grid(ceil_div(T, 256), C / 2, B);
+  affine_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, params, g_y, g_log_s, C / 2, T, scaling, g_z, g_params);
+  return after_launch();
+}
+
+extern "C" int radtts_pointwise_conv_small_backward(const float* x, const float* w, const float* g_y, int B, int C, int T,
+                                                    float* g_x, float* g_w, void* stream) {
+  if (!x || !w || !g_y || !g_x || !g_w || B <= 0 || C <= 0 || T <= 0) return RADTTS_ERR_INVALID_ARG;
+  if (C > 16) return RADTTS_ERR_UNSUPPORTED;
+  RB_CUDA(cudaMemsetAsync(g_w, 0, (size_t)C * C * sizeof(float), (cudaStream_t)stream));
+  dim3 grid(ceil_div(T, 256), B);
+  pointwise_small_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, g_y, C, T, g_x, g_w);
   return after_launch();
 }

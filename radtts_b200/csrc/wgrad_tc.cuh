@@ -31,6 +31,10 @@ struct WgTcParams {
   const int* plan;
 };
 
+// The kernel has ONE definition in the library (flow_bwd.cu defines RB_WGRAD_TC_DEFINE before including this header);
+// other translation units (convnet.cu) launch it through this declaration.
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgTcParams p);
+#ifdef RB_WGRAD_TC_DEFINE
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -155,6 +159,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     tmem_dealloc<512>(tmem_base);
   }
 }
+
+#endif  // RB_WGRAD_TC_DEFINE
 
 // Host-side batch builder ----------------------------------------------------------------------------------
 struct WgradBatch {

@@ -763,71 +763,8 @@ def _needs_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
-# Training direction of the BGAP attribute flows.  The fused kernels below (csrc/convnet.cu, spline.cu)
-# are forward-only; when a gradient is needed these functions run the same math as differentiable GPU library ops
-# (cuDNN convs, element-wise kernels), so that `config_ljs_bgap` trains end to end on the device.  The tensors are small
-# (B x <=8 channels x T for the flow variables, 33 parameters per transformed scalar): this is not the step's hot path.
-def _scale_and_log(x, scaling):
-    """reference common.py:775-808."""
-    if scaling == "tanh":
-        s = (torch.tanh(x) + 1.0) + 1e-6
-        return s, torch.log(s)
-    if scaling == "exp":
-        return torch.exp(x), x
-    if scaling == "sigmoid":
-        s = torch.sigmoid(x + 10.0) + 1e-6
-        return s, torch.log(s)
-    if scaling == "translate":
-        return torch.ones_like(x), torch.zeros_like(x)
-    raise NotImplementedError("scaling_fn %r" % (scaling,))
-
-
-def _simple_conv_net_autograd(net, x, seq_lens):
-    """SimpleConvNet.forward (reference common.py:503-515) through the ConvNorm / PartialConv1d module mirrors."""
-    mask = None
-    if seq_lens is not None:
-        mask = (torch.arange(x.shape[2], device=x.device)[None, :] < seq_lens.to(x.device)[:, None])[:, None].to(x.dtype)
-    for layer in net.layers:
-        x = torch.relu(layer(x, mask))
-    return net.last_layer(x)
-
-
-def _rq_spline_autograd(x, w_tilde, v_tilde, inverse):
-    """splines.py:221-319 (unbounded piecewise-quadratic transform) without boolean-index gathers: evaluated for every
-    element on a clamped copy of x and selected with torch.where, so there is no host synchronisation and the
-    gradient of elements outside [0, 1) is exactly the identity's."""
-    eps = torch.finfo(x.dtype).eps
-    inside = (x >= 0) & (x < 1)
-    xc = torch.where(inside, x, torch.full_like(x, 0.5))
-    w = torch.softmax(w_tilde, dim=-1)
-    v = torch.exp(v_tilde - v_tilde.max(dim=-1, keepdim=True)[0]) + 1e-8
-    v = v / (((v[..., :-1] + v[..., 1:]) / 2) * w).sum(-1, keepdim=True)
-    wc = torch.cumsum(w, -1)
-    wc = torch.cat((wc[..., :-1], torch.ones_like(wc[..., -1:])), -1)
-    wc0 = torch.nn.functional.pad(wc, (1, 0))
-    cdf = torch.cumsum((v[..., 1:] + v[..., :-1]) / 2 * w, -1)
-    cdf = torch.cat((cdf[..., :-1], torch.ones_like(cdf[..., -1:])), -1)
-    cdf0 = torch.nn.functional.pad(cdf, (1, 0))
-    knots = cdf if inverse else wc
-    idx = torch.searchsorted(knots.detach(), xc.detach().unsqueeze(-1)).clamp(max=w.shape[-1] - 1)
-    take = lambda t, i: torch.gather(t, -1, i).squeeze(-1)
-    w_b, w_lo = take(w, idx), take(wc0, idx)
-    v_b, v_n = take(v, idx), take(v, idx + 1)
-    c_lo = take(cdf0, idx)
-    if not inverse:
-        alpha = (xc - w_lo) / w_b.clamp(min=eps)
-        out = alpha ** 2 / 2 * (v_n - v_b) * w_b + alpha * v_b * w_b + c_lo
-        log_j = torch.lerp(v_b, v_n, alpha).clamp(min=eps).log()
-        out = out.clamp(min=eps, max=1.0 - eps)
-        return torch.where(inside, out, x), torch.where(inside, log_j, torch.zeros_like(log_j))
-    qa = (v_n - v_b) * w_b / 2
-    qb = v_b * w_b
-    qc = c_lo - xc
-    alpha = (-qb + torch.sqrt(qb ** 2 - 4 * qa * qc)) / (2 * qa)
-    out = (alpha * w_b + w_lo).clamp(min=eps, max=1.0 - eps)
-    return torch.where(inside, out, x), None
-
-
+# Training direction of the BGAP attribute flows: the parameter networks run on the packed-row conv kernels in
+# both directions (_ConvStackFn), the spline / affine transforms and the small 1x1 convs have closed-form backward kernels.
 class _SplineForwardFn(torch.autograd.Function):
     """Forward-direction spline coupling apply (radtts_rqspline_apply) with the closed-form backward kernel
     (radtts_rqspline_backward): z (B, C, T), params (B, h (2 nb + 1), T) -> (y, log_s)."""
@@ -863,54 +800,80 @@ class _SplineForwardFn(torch.autograd.Function):
         return g_z, g_p, None, None, None, None, None
 
 
-def _spline_coupling_autograd(layer, z, context, inverse, seq_lens):
-    """SplineTransformationLayer.forward, use_quadratic=True (reference common.py:694-743)."""
-    import math
-    b, c, t = z.shape
-    h = layer.half_mel_channels
-    if not inverse and z.is_cuda and not os.environ.get("RADTTS_SPLINE_AUTOGRAD"):
-        # parameter network on differentiable library ops, the spline itself on the fused kernels (forward + closed-form
-        # backward); z[:, :h] reaches the parameters through autograd, the Function returns the direct path
-        q = _simple_conv_net_autograd(layer.param_predictor, torch.cat((z[:, :h], context), 1), seq_lens)
-        return _SplineForwardFn.apply(z, q, layer.n_bins // 2, float(layer.left), float(layer.right),
-                                      float(layer.bottom), float(layer.top))
-    z0, z1 = z[:, :h], z[:, h:]
-    z1 = (z1 - layer.bottom) / (layer.top - layer.bottom) if inverse else (z1 - layer.left) / (layer.right - layer.left)
-    nb = layer.n_bins
-    q = _simple_conv_net_autograd(layer.param_predictor, torch.cat((z0, context), 1), seq_lens)
-    q = q.permute(0, 2, 1).reshape(b * t, h, nb).float()
-    x = z1.permute(0, 2, 1).reshape(b * t, h).float()
-    y, log_j = _rq_spline_autograd(x, q[..., :nb // 2], q[..., nb // 2:], inverse)
-    y = y.reshape(b, t, h).permute(0, 2, 1)
-    if inverse:
-        return torch.cat((z0, y * (layer.right - layer.left) + layer.left), 1)
-    y = y * (layer.top - layer.bottom) + layer.bottom
-    log_s = log_j.sum(1).reshape(b, t)[:, None] + h * (math.log(layer.top - layer.bottom) - math.log(layer.right - layer.left))
-    return torch.cat((z0, y), 1), log_s
+class _AffineForwardFn(torch.autograd.Function):
+    """Forward-direction affine coupling apply (radtts_affine_apply) with its closed-form backward kernel
+    (radtts_affine_backward): z (B, C, T), params (B, C, T) = [raw scale | translation] -> (y, log_s (B, C/2, T))."""
+
+    @staticmethod
+    def forward(ctx, z, params, scaling):
+        z = z.float().contiguous()
+        params = params.float().contiguous()
+        B, C, T = z.shape
+        y = torch.empty_like(z)
+        log_s = torch.empty((B, C // 2, T), dtype=torch.float32, device=z.device)
+        _lib.check(_lib.lib().radtts_affine_apply(_lib.ptr(z), _lib.ptr(params), B, C, T, scaling, 0, _lib.ptr(y),
+                                                  _lib.ptr(log_s), _lib.stream_of(z)), "radtts_affine_apply")
+        ctx.save_for_backward(z, params)
+        ctx.scaling = scaling
+        return y, log_s
+
+    @staticmethod
+    def backward(ctx, g_y, g_log_s):
+        z, params = ctx.saved_tensors
+        B, C, T = z.shape
+        g_y = None if g_y is None else g_y.float().contiguous()
+        g_log_s = None if g_log_s is None else g_log_s.float().contiguous()
+        g_z = torch.empty_like(z)
+        g_p = torch.empty_like(params)
+        _lib.check(_lib.lib().radtts_affine_backward(_lib.ptr(z), _lib.ptr(params), _lib.ptr(g_y), _lib.ptr(g_log_s), B, C, T,
+                                                     ctx.scaling, _lib.ptr(g_z), _lib.ptr(g_p), _lib.stream_of(z)),
+                   "radtts_affine_backward")
+        return g_z, g_p, None
 
 
-def _affine_coupling_autograd(layer, z, context, inverse, seq_lens):
-    """AffineTransformationLayer.forward with affine_model='simple_conv' (reference common.py:810-832)."""
-    h = z.shape[1] // 2
-    z0, z1 = z[:, :h], z[:, h:]
-    params = _simple_conv_net_autograd(layer.affine_param_predictor, torch.cat((z0, context), 1), seq_lens)
-    s, log_s = _scale_and_log(params[:, :h], layer.scaling_fn)
-    bias = params[:, h:]
-    if inverse:
-        return torch.cat((z0, (z1 - bias) / s), 1)
-    return torch.cat((z0, s * z1 + bias), 1), log_s
+def _training_direction_only(what):
+    raise NotImplementedError("%s: gradients are implemented for the training (forward) direction only; run the sampling "
+                              "direction under torch.no_grad()" % what)
+
+
+class _PointwiseSmallFn(torch.autograd.Function):
+    """y[b,:,t] = W x[b,:,t] for the small dense 1x1 convs of the attribute flows (C <= 16), forward and backward kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x = x.float().contiguous()
+        w = w.float().contiguous()
+        B, C, T = x.shape
+        y = torch.empty_like(x)
+        _lib.check(_lib.lib().radtts_pointwise_conv_small(_lib.ptr(x), _lib.ptr(w), B, C, T, _lib.ptr(y), _lib.stream_of(x)),
+                   "radtts_pointwise_conv_small")
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x, w = ctx.saved_tensors
+        B, C, T = x.shape
+        g_y = g_y.float().contiguous()
+        g_x = torch.empty_like(x)
+        g_w = torch.empty_like(w)
+        _lib.check(_lib.lib().radtts_pointwise_conv_small_backward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(g_y), B, C, T,
+                                                                   _lib.ptr(g_x), _lib.ptr(g_w), _lib.stream_of(x)),
+                   "radtts_pointwise_conv_small_backward")
+        return g_x, g_w
 
 
 def pointwise_conv(z, w):
     """y[b,:,t] = W z[b,:,t] (Invertible1x1Conv / Invertible1x1ConvLUS module API on reference-shaped tensors)."""
     _lib.require_cuda(z, w)
-    if _needs_grad(z, w):
-        return torch.matmul(w.float(), z.float())   # differentiable library op (training direction of the attribute flows)
-    z = z.float().contiguous()
-    w = w.detach().float().contiguous()
     B, C, T = z.shape
     if C > 16:
-        return torch.matmul(w, z)   # large-C 1x1 convs on the hot path go through ops.flow_step instead
+        # large-C 1x1 convs on the hot path go through ops.flow_step; this module-level call is a plain library GEMM
+        return torch.matmul(w.float(), z.float())
+    if _needs_grad(z, w):
+        return _PointwiseSmallFn.apply(z, w)
+    z = z.float().contiguous()
+    w = w.detach().float().contiguous()
     y = torch.empty_like(z)
     _lib.check(_lib.lib().radtts_pointwise_conv_small(_lib.ptr(z), _lib.ptr(w), B, C, T, _lib.ptr(y), _lib.stream_of(z)),
                "radtts_pointwise_conv_small")
@@ -948,22 +911,153 @@ def _pad64(n):
     return (n + 63) // 64 * 64
 
 
+_ACT_CODES = {"none": 0, "softplus": 1, "relu": 2}
+
+
+class ConvStackSpec:
+    """Static description of a stack of ConvNorm layers on packed rows: per layer (ksize, dilation, act code, partial,
+    mask_rows), whether every utterance physically keeps all T rows (plain, non-partial stacks read the padded region,
+    reference common.py:145-154) and whether the packed input is zeroed past the valid length (partial convs)."""
+
+    def __init__(self, layers, geom_full, valid_only):
+        self.layers, self.geom_full, self.valid_only = tuple(layers), bool(geom_full), bool(valid_only)
+
+
+def _prepare_conv_raw(w, b, c_in_pad, prec):
+    L = _lib.lib()
+    c_out, c_in, k = w.shape
+    nbytes = int(L.radtts_conv_prepared_bytes(c_out, c_in_pad, k, prec))
+    blob = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    wf = w.detach().float().contiguous()
+    bf = None if b is None else b.detach().float().contiguous()
+    _lib.check(L.radtts_conv_prepare(_lib.ptr(wf), _lib.ptr(bf), c_out, c_in, c_in_pad, k, prec, _lib.ptr(blob),
+                                     ctypes.c_size_t(nbytes), _lib.stream_of(w)), "radtts_conv_prepare")
+    return blob
+
+
+class _ConvStackFn(torch.autograd.Function):
+    """x (B, C, T) -> (B, C_out, T) through a stack of conv layers, every layer ONE row-GEMM launch with a fused
+    bias / partial-conv ratio / activation epilogue (radtts_conv_rows) -- and the backward on the same engines
+    (radtts_conv_rows_backward: transposed-tap dgrad GEMM, one tcgen05 weight-gradient problem per tap with K = packed
+    rows, streaming bias column sums).  params = (w_0, b_0, w_1, b_1, ...) in the reference's (c_out, c_in, k) layout."""
+
+    @staticmethod
+    def forward(ctx, x, seq_lens, spec, prec, *params):
+        B, C, T = x.shape
+        dev = x.device
+        act = _act_dtype(prec)
+        lens = seq_lens if seq_lens is not None else torch.full((B,), T, dtype=torch.int64, device=dev)
+        geom = torch.full((B,), T, dtype=torch.int64, device=dev) if spec.geom_full else None
+        plan = FramePlan(lens.to(dev), 1, T, geom)
+        L = _lib.lib()
+        stream = _lib.stream_of(x)
+        lease = _Lease()
+        cur = pack_frames(x, plan, 1, act, _pad64(C), 0, _pad64(C), valid_only=spec.valid_only)
+        acts = [cur]
+        for i, (k, dil, act_code, partial, mask_rows) in enumerate(spec.layers):
+            w, b = params[2 * i], params[2 * i + 1]
+            c_out, c_in, kk = w.shape
+            cur_w = acts[-1].shape[1]
+            blob = _prepare_conv_raw(w, b, cur_w, prec)
+            out_w = _pad64(c_out)
+            out = lease.take("y%d" % i, (plan.rows, out_w), act, dev)
+            _lib.check(L.radtts_conv_rows(_lib.ptr(blob), c_out, cur_w, kk, dil, act_code, partial, mask_rows,
+                                          _lib.ptr(acts[-1]), cur_w, _lib.ptr(out), out_w, 0, plan.ptr, plan.B, plan.Tmax,
+                                          prec, stream), "radtts_conv_rows")
+            acts.append(out)
+        c_last = params[2 * (len(spec.layers) - 1)].shape[0]
+        last = acts[-1]
+        res = unpack_frames(last.float() if last.dtype != torch.float32 else last, plan, c_last, 1, 0)
+        if any(ctx.needs_input_grad):
+            ctx.saved = (plan, spec, prec, acts, lease, params, (B, C, T))
+        else:
+            lease.release()
+        return res
+
+    @staticmethod
+    def backward(ctx, g):
+        plan, spec, prec, acts, lease, params, (B, C, T) = ctx.saved
+        ctx.saved = None
+        dev = g.device
+        act = _act_dtype(prec)
+        L = _lib.lib()
+        stream = _lib.stream_of(g)
+        scratch = _Lease()
+        n_layers = len(spec.layers)
+        c_last = params[2 * (n_layers - 1)].shape[0]
+        g_y = pack_frames(g.contiguous(), plan, 1, act, _pad64(c_last), 0, _pad64(c_last))
+        grads = [None] * len(params)
+        need_x = ctx.needs_input_grad[0]
+        for i in reversed(range(n_layers)):
+            k, dil, act_code, partial, mask_rows = spec.layers[i]
+            w, b = params[2 * i], params[2 * i + 1]
+            c_out, c_in, kk = w.shape
+            x_i, y_i = acts[i], acts[i + 1]
+            c_in_pad = x_i.shape[1]
+            nbytes = int(L.radtts_conv_backward_prepared_bytes(c_out, c_in_pad, kk, prec))
+            blob_t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            wf = w.detach().float().contiguous()
+            _lib.check(L.radtts_conv_prepare_backward(_lib.ptr(wf), c_out, c_in, c_in_pad, kk, prec, _lib.ptr(blob_t),
+                                                      ctypes.c_size_t(nbytes), stream), "radtts_conv_prepare_backward")
+            g_pre = scratch.take("g_pre%d" % i, (plan.rows, _pad64(c_out)), act, dev)
+            g_x = scratch.take("g_x%d" % i, (plan.rows, c_in_pad), act, dev) if (i > 0 or need_x) else None
+            g_w = torch.empty((c_out, c_in, kk), dtype=torch.float32, device=dev)
+            g_b = None if b is None else torch.empty((c_out + 15) // 16 * 16, dtype=torch.float32, device=dev)
+            _lib.check(L.radtts_conv_rows_backward(_lib.ptr(blob_t), c_out, c_in, c_in_pad, kk, dil, act_code, partial,
+                                                   mask_rows, _lib.ptr(x_i), c_in_pad, _lib.ptr(y_i), y_i.shape[1], 0,
+                                                   _lib.ptr(g_y), g_y.shape[1], _lib.ptr(g_pre), _lib.ptr(g_x), c_in_pad,
+                                                   _lib.ptr(g_w), _lib.ptr(g_b), plan.ptr, plan.B, plan.Tmax, prec, stream),
+                       "radtts_conv_rows_backward")
+            grads[2 * i] = g_w.to(w.dtype)
+            if b is not None:
+                grads[2 * i + 1] = g_b[:c_out].to(b.dtype)
+            g_y = g_x
+        g_in = None
+        if need_x:
+            gx = g_y.float() if g_y.dtype != torch.float32 else g_y
+            g_in = unpack_frames(gx.contiguous(), plan, C, 1, 0)
+            if g_in.shape[2] != T:
+                g_in = torch.nn.functional.pad(g_in, (0, T - g_in.shape[2]))
+        scratch.release()
+        lease.release()
+        return (g_in, None, None, None) + tuple(grads)
+
+
+def conv_stack(x, seq_lens, spec, params, prec=None):
+    prec = current_precision() if prec is None else prec
+    return _ConvStackFn.apply(x.float(), seq_lens, spec, prec, *params)
+
+
+def _simple_conv_net_spec(net):
+    layers = [(layer.conv.kernel_size[0], layer.dilation, _ACT_CODES["relu"], int(net.use_partial_padding), 1)
+              for layer in net.layers]
+    layers.append((1, 1, _ACT_CODES["none"], 0, 0))
+    # The reference runs these nets over the whole zero-padded batch: plain (non-partial) ConvNorm layers read the padded
+    # region in their first layer and `last_layer` is not masked (common.py:145-154,514) -> every utterance keeps all T rows
+    return ConvStackSpec(layers, geom_full=True, valid_only=bool(net.use_partial_padding))
+
+
 def simple_conv_net(net, x, seq_lens):
     """SimpleConvNet.forward (reference common.py:503-515) on packed rows: n_layers x [ConvNorm (+partial padding) ->
-    ReLU] then the 1x1 `last_layer`; every layer is one row-GEMM launch with a fused epilogue."""
+    ReLU] then the 1x1 `last_layer`; every layer is one row-GEMM launch with a fused epilogue, in both directions."""
     _lib.require_cuda(x)
-    if _needs_grad(x, *net.parameters()):
-        return _simple_conv_net_autograd(net, x, seq_lens)
+    params = []
+    for layer in net.layers:
+        params += [layer.conv.weight, layer.conv.bias]
+    params += [net.last_layer.weight, net.last_layer.bias]
+    if not _needs_grad(x, *params):
+        return _simple_conv_net_cached(net, x, seq_lens)
+    return conv_stack(x, seq_lens, _simple_conv_net_spec(net), params)
+
+
+def _simple_conv_net_cached(net, x, seq_lens):
+    """Inference: as conv_stack's forward, with the re-laid-out weights cached on the modules (frozen weights)."""
     B, C, T = x.shape
     prec = current_precision()
     act = _act_dtype(prec)
     dev = x.device
     if seq_lens is None:
         seq_lens = torch.full((B,), T, dtype=torch.int64, device=dev)
-    # The reference runs these nets over the whole zero-padded batch: plain (non-partial) ConvNorm layers read the
-    # padded region in their first layer and `last_layer` is not masked (common.py:145-154,514), so values in the
-    # padded region feed back into valid frames of later flows.  To stay identical, every utterance physically keeps
-    # all T rows; validity (the `* mask` after each ConvNorm, the partial-conv counts) still follows seq_lens.
     geom = torch.full((B,), T, dtype=torch.int64, device=dev)
     plan = FramePlan(seq_lens.to(dev), 1, T, geom)
     L = _lib.lib()
@@ -996,12 +1090,15 @@ def affine_coupling(layer, z, context, inverse, seq_lens):
     scaling = layer.scaling_fn
     if isinstance(scaling, list) or scaling not in _SCALING:
         raise NotImplementedError("per-channel scaling_fn lists are not supported")
-    if _needs_grad(z, context, *layer.affine_param_predictor.parameters()):
-        return _affine_coupling_autograd(layer, z.float(), context.float(), inverse, seq_lens)
     z = z.float().contiguous()
     B, C, T = z.shape
     h = C // 2
     params = simple_conv_net(layer.affine_param_predictor, torch.cat((z[:, :h], context.float()), 1), seq_lens)
+    if _needs_grad(z, params):
+        if inverse:
+            _training_direction_only("affine coupling")
+        # the parameter net (conv_stack) reaches z[:, :h] and the context through autograd; the Function adds the direct path
+        return _AffineForwardFn.apply(z, params, _SCALING[scaling])
     y = torch.empty_like(z)
     log_s = None if inverse else torch.empty((B, h, T), dtype=torch.float32, device=z.device)
     _lib.check(_lib.lib().radtts_affine_apply(_lib.ptr(z), _lib.ptr(params.contiguous()), B, C, T, _SCALING[scaling],
@@ -1013,13 +1110,16 @@ def affine_coupling(layer, z, context, inverse, seq_lens):
 def spline_coupling(layer, z, context, inverse, seq_lens):
     """SplineTransformationLayer.forward with use_quadratic=True (reference common.py:694-743, splines.py:221-319)."""
     _lib.require_cuda(z, context)
-    if _needs_grad(z, context, *layer.param_predictor.parameters()):
-        return _spline_coupling_autograd(layer, z.float(), context.float(), inverse, seq_lens)
     z = z.float().contiguous()
     B, C, T = z.shape
     h = layer.half_mel_channels
     params = simple_conv_net(layer.param_predictor, torch.cat((z[:, :h], context.float()), 1), seq_lens).contiguous()
     n_bins = layer.n_bins // 2
+    if _needs_grad(z, params):
+        if inverse:
+            _training_direction_only("spline coupling")
+        return _SplineForwardFn.apply(z, params, n_bins, float(layer.left), float(layer.right), float(layer.bottom),
+                                      float(layer.top))
     y = torch.empty_like(z)
     log_s = None if inverse else torch.empty((B, 1, T), dtype=torch.float32, device=z.device)
     _lib.check(_lib.lib().radtts_rqspline_apply(_lib.ptr(z), _lib.ptr(params), B, C, T, n_bins, int(bool(inverse)),
@@ -1068,15 +1168,34 @@ class _ConvAttnFn(torch.autograd.Function):
         return g_q, g_k, None, None, None
 
 
+def _projection_stack(seq, x):
+    """An nn.Sequential of ConvNorm / ReLU modules (ConvAttention.key_proj / query_proj, reference common.py:843-858)
+    as one conv_stack call: plain zero-padded convs over the whole padded batch (no length masks, as in the reference)."""
+    layers, params = [], []
+    mods = list(seq)
+    for i, m in enumerate(mods):
+        if isinstance(m, torch.nn.ReLU):
+            continue
+        conv = m.conv
+        if hasattr(conv, "weight_v") or conv.stride[0] != 1 or conv.padding[0] != conv.dilation[0] * (conv.kernel_size[0] - 1) // 2:
+            return None
+        relu = i + 1 < len(mods) and isinstance(mods[i + 1], torch.nn.ReLU)
+        layers.append((conv.kernel_size[0], conv.dilation[0], _ACT_CODES["relu" if relu else "none"], 0, 0))
+        params += [conv.weight, conv.bias]
+    return conv_stack(x, None, ConvStackSpec(layers, geom_full=True, valid_only=False), params)
+
+
 def conv_attention(att, queries, keys, mask, key_lens, attn_prior):
-    """ConvAttention.forward (reference common.py:886-924).  The key/query projections are five small convs
-    (< 0.5 % of the step's FLOPs) run through cuDNN (bf16 under autocast); everything after them -- the part that dominates memory
-    traffic in the reference -- is the fused CUDA kernel 3."""
+    """ConvAttention.forward (reference common.py:886-924), all of it in the library: the key / query projections are
+    conv_stack calls (row GEMMs on the tcgen05 engine under autocast, exactly where the reference's convs would run in
+    half precision; fp32 SIMT otherwise) with their backward on the same engines, and everything after them -- the part that
+    dominates memory traffic in the reference -- is the fused distance / log-softmax / prior / softmax kernel."""
     _lib.require_cuda(queries, keys)
-    # the projections follow the ambient autocast state exactly as in the reference (common.py:900-901: only the
-    # softmax / log part is forced to fp32); the fused kernel takes their outputs in fp32
-    k_enc = att.key_proj(keys).float()
-    q_enc = att.query_proj(queries).float()
+    k_enc = _projection_stack(att.key_proj, keys)
+    q_enc = _projection_stack(att.query_proj, queries)
+    if k_enc is None or q_enc is None:    # a projection this build does not recognise (weight norm, strides): library convs
+        k_enc = att.key_proj(keys).float()
+        q_enc = att.query_proj(queries).float()
     if key_lens is None and mask is not None:
         key_lens = (~mask.squeeze(-1)).sum(1)
     if mask is None:

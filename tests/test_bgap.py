@@ -121,3 +121,85 @@ def test_cuda_bgap_training_direction_gradients_match_reference(gold, model_and_
         p = params[str(pn)]
         assert p.grad is not None, pn
         check(p.grad, gold["%s_gp_%d_summary" % (name, i)], gold["%s_gp_%d_sample" % (name, i)], str(pn))
+
+
+def _torch_simple_conv_net(net, x, seq_lens):
+    """SimpleConvNet.forward (reference common.py:503-515) through the ConvNorm / PartialConv1d module mirrors (torch ops)."""
+    mask = (torch.arange(x.shape[2], device=x.device)[None, :] < seq_lens.to(x.device)[:, None])[:, None].to(x.dtype)
+    for layer in net.layers:
+        x = torch.relu(layer(x, mask))
+    return net.last_layer(x)
+
+
+@pytest.mark.parametrize("partial", [True, False])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_conv_stack_forward_and_backward_match_torch(partial, prec, cuda_lib):
+    """radtts_conv_rows / radtts_conv_rows_backward (packed-row GEMMs, both engines) against cuDNN/ATen autograd on the
+    same SimpleConvNet: output, input gradient and every weight / bias gradient, ragged lengths, dilations 1..8."""
+    from radtts_b200.common import SimpleConvNet
+    torch.manual_seed(7)
+    net = SimpleConvNet(2, 80, 66, n_layers=4, zero_init=False, use_partial_padding=partial).cuda()
+    B, T = 5, 93
+    lens = torch.tensor([93, 80, 61, 33, 7], device="cuda")
+    x = torch.randn(B, 82, T, device="cuda")
+    g = torch.randn(B, 66, T, device="cuda")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        xr = x.clone().requires_grad_(True)
+        yr = _torch_simple_conv_net(net, xr, lens)
+        (yr * g).sum().backward()
+        want = {n: p.grad.clone() for n, p in net.named_parameters()}
+        want_x = xr.grad.clone()
+        net.zero_grad()
+        ops.set_precision(prec)
+        xg = x.clone().requires_grad_(True)
+        y = ops.simple_conv_net(net, xg, lens)
+        (y * g).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        ops.set_precision(None)
+    tol = 2e-4 if prec == "fp32" else 4e-2
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-20))   # noqa: E731
+    assert rel(y.detach(), yr.detach()) < tol
+    assert rel(xg.grad, want_x) < tol
+    for n, p in net.named_parameters():
+        assert p.grad is not None, n
+        assert rel(p.grad, want[n]) < tol, (n, rel(p.grad, want[n]))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_attention_projections_on_library_kernels_match_torch(prec, cuda_lib):
+    """ConvAttention.key_proj / query_proj (reference common.py:843-858,903-905) through ops.conv_stack vs the nn modules."""
+    from radtts_b200.common import ConvAttention
+    torch.manual_seed(9)
+    att = ConvAttention(80, 512, 80).cuda()
+    keys = torch.randn(3, 512, 37, device="cuda")
+    queries = torch.randn(3, 80, 150, device="cuda")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for seq, x in ((att.key_proj, keys), (att.query_proj, queries)):
+            xr = x.clone().requires_grad_(True)
+            yr = seq(xr)
+            g = torch.randn_like(yr)
+            (yr * g).sum().backward()
+            want = {n: p.grad.clone() for n, p in seq.named_parameters()}
+            seq.zero_grad()
+            ops.set_precision(prec)
+            xg = x.clone().requires_grad_(True)
+            y = ops._projection_stack(seq, xg)
+            (y * g).sum().backward()
+            ops.set_precision(None)
+            tol = 2e-4 if prec == "fp32" else 4e-2
+            rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-20))   # noqa: E731
+            assert rel(y.detach(), yr.detach()) < tol
+            assert rel(xg.grad, xr.grad) < tol
+            for n, p in seq.named_parameters():
+                assert rel(p.grad, want[n]) < tol, (n, rel(p.grad, want[n]))
+            seq.zero_grad()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        ops.set_precision(None)

@@ -1,14 +1,14 @@
 """CPU checks of host-side pieces that are plain tensor programs (no CUDA library involved): the vectorised
-LengthRegulator against the reference's per-token loop semantics (common.py:171-200), and the differentiable spline /
-coupling formulation used for the attribute flows' training direction against the oracle restatement of
-splines.py:221-319."""
+LengthRegulator against the reference's per-token loop semantics (common.py:171-200), and the oracle's two spline
+restatements (closed-form gradients vs the differentiable torch formulation of splines.py:221-319) against each other --
+the closed form is the blueprint of the CUDA backward kernel."""
 import math
 
 import pytest
 import torch
 
 from oracle import flow as oflow
-from radtts_b200 import ops
+from oracle import spline_grad
 from radtts_b200.common import LengthRegulator
 
 
@@ -37,7 +37,7 @@ def test_spline_autograd_formulation_matches_oracle(inverse):
     want, want_lj = oflow.rq_spline_unbounded(x.clone(), w, v, inverse)
     xg = x.clone().requires_grad_(True)
     wg, vg = w.clone().requires_grad_(True), v.clone().requires_grad_(True)
-    got, got_lj = ops._rq_spline_autograd(xg, wg, vg, inverse)
+    got, got_lj = spline_grad.rq_spline_autograd(xg, wg, vg, inverse)
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
     if not inverse:
         assert torch.allclose(got_lj, want_lj, rtol=1e-5, atol=1e-6)
@@ -51,22 +51,8 @@ def test_spline_autograd_formulation_matches_oracle(inverse):
     assert float(wg.grad[outside].abs().max()) == 0.0
 
 
-def test_scale_and_log_modes():
-    x = torch.linspace(-3, 3, 13)
-    s, ls = ops._scale_and_log(x, "tanh")
-    assert torch.allclose(s, torch.tanh(x) + 1 + 1e-6) and torch.allclose(ls, torch.log(s))
-    s, ls = ops._scale_and_log(x, "exp")
-    assert torch.allclose(s, torch.exp(x)) and torch.equal(ls, x)
-    s, ls = ops._scale_and_log(x, "sigmoid")
-    assert torch.allclose(s, torch.sigmoid(x + 10) + 1e-6)
-    s, ls = ops._scale_and_log(x, "translate")
-    assert float(s.min()) == 1.0 and float(ls.abs().max()) == 0.0
-    assert math.isfinite(float(ls.sum()))
-
-
 def test_analytic_spline_backward_matches_autograd():
     """oracle/spline_grad.py (closed-form gradients, the blueprint for a spline-backward kernel) vs autograd, float64."""
-    from oracle import spline_grad
     torch.manual_seed(3)
     n, k = 400, 16
     x = (torch.rand(n, dtype=torch.float64) * 1.5 - 0.25)
@@ -74,7 +60,7 @@ def test_analytic_spline_backward_matches_autograd():
     v = torch.randn(n, k + 1, dtype=torch.float64)
     gy, gl = torch.randn(n, dtype=torch.float64), torch.randn(n, dtype=torch.float64)
     xg, wg, vg = x.clone().requires_grad_(True), w.clone().requires_grad_(True), v.clone().requires_grad_(True)
-    y, lj = ops._rq_spline_autograd(xg[:, None], wg[:, None, :], vg[:, None, :], False)
+    y, lj = spline_grad.rq_spline_autograd(xg[:, None], wg[:, None, :], vg[:, None, :], False)
     ((y[:, 0] * gy).sum() + (lj[:, 0] * gl).sum()).backward()
     y2, lj2, g_x, g_w, g_v = spline_grad.rq_spline_forward_backward(x, w, v, gy, gl)
     assert torch.allclose(y2, y[:, 0].detach(), rtol=1e-12, atol=1e-12)

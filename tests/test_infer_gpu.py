@@ -108,6 +108,9 @@ def test_batched_predictors_equal_per_utterance_runs(cuda_lib):
     for b in range(B):
         txt[b, :, lens[b]:] = 0
     ops.set_precision("fp32")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False      # TF32 GEMMs round differently for different batch sizes
+    torch.backends.cuda.matmul.allow_tf32 = False
     try:
         with torch.no_grad():
             for mod in (m.dur_pred_layer, m.v_pred_module):
@@ -118,6 +121,7 @@ def test_batched_predictors_equal_per_utterance_runs(cuda_lib):
                     single = mod.infer(None, txt[b:b + 1, :, :n], spk[b:b + 1], lens=None)
                     assert torch.allclose(batched[b:b + 1, :, :n], single, rtol=1e-4, atol=1e-5), (type(mod).__name__, b)
     finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
         ops.set_precision(None)
 
 
@@ -147,6 +151,9 @@ def test_batched_infer_with_in_lens_equals_per_utterance_infer(cuda_lib, monkeyp
     monkeypatch.setattr(rmod, "_noise", noise)
     spk = torch.zeros(B, dtype=torch.long, device="cuda")
     ops.set_precision("fp32")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     try:
         with torch.no_grad():
             out = m.infer(spk, text, 0.8, dur=dur, in_lens=in_lens)
@@ -160,4 +167,5 @@ def test_batched_infer_with_in_lens_equals_per_utterance_infer(cuda_lib, monkeyp
                     a, r = out[k][b][..., :t], one[k][0][..., :t]
                     assert torch.allclose(a, r, rtol=2e-3, atol=tol), (k, b, float((a - r).abs().max()))
     finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
         ops.set_precision(None)
