@@ -447,6 +447,7 @@ def train_leg(name, args, world, rank, local, device, steps, with_attributes=Fal
             graph_note = "cuda_graph"
         except Exception as e:  # fall back to the eager step, say so in the JSON line
             graph_note = "eager (graph capture failed: %s)" % str(e).splitlines()[0][:120]
+            print("graph capture failed for %s: %r" % (name, e), file=sys.stderr)
             torch.cuda.synchronize()
             ts.graph = None
     frames_local = float(sum(int(b["out_lens"].sum()) for b in host_batches)) / len(host_batches)

@@ -322,7 +322,8 @@ static int launch_fwd(const float* q, const float* k, const float* prior, const 
   // ~2 CTAs per SM in total; every CTA of an utterance stages its keys once and walks its share of the frame tiles
   // sized to ONE resident wave (1 or 2 CTAs per SM, whatever the key stage leaves room for)
   const int n_tiles = ceil_div(T1, kFwdRows);
-  const int per_sm = (2 * (smem + 1024) <= (size_t)233472) ? 2 : 1;
+  int per_sm = (int)((size_t)233472 / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2048 / kFwdThreads ? 2048 / kFwdThreads : per_sm);
   int per_utt = per_sm * kNumSMs / B;
   per_utt = per_utt < 1 ? 1 : (per_utt > n_tiles ? n_tiles : per_utt);
   dim3 grid(per_utt, B);

@@ -86,8 +86,15 @@ class TrainStep:
 
     def _probe_used(self, batch):
         self.raw_model.zero_grad(set_to_none=True)
-        total, _ = self.forward_loss(batch)
-        total.backward()
+        # on a side stream, like capture()'s warm-up: autograd nodes remember the stream they were created on, and an eager
+        # backward on the legacy default stream before a capture makes the captured backward fail (implicit-sync error)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            total, _ = self.forward_loss(batch)
+            total.backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
         used = {id(p) for p in self.raw_model.parameters() if p.grad is not None}
         self.raw_model.zero_grad(set_to_none=True)
         self.criterion.attn_ctc_loss._prefetched = None
