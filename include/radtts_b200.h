@@ -359,6 +359,10 @@ RADTTS_API int radtts_lstm_backward(const float* dh_all, const float* whh, const
                                     const float* c_save, int T, int B, int H, float* dgates_all, void* ws,
                                     size_t ws_bytes, int precision, void* stream);
 
+/* Diagnostic: phase cycle sums (clock64) of cluster rank 0 of the last cluster-LSTM launch, SIXTEEN host words: forward
+ * [0] waiting for h, [1] MMAs, [2] gates + staging, [4] send + output stores, [5] steps.  Synchronises the device. */
+RADTTS_API int radtts_lstm_debug_timeline(unsigned long long* out16_host);
+
 /* ------------------------------------------------------------------------------------------------
  * Attention CTC loss, fused.  Replaces AttentionCTCLoss.forward (reference loss.py:118-135): blank
  * logit + per-utterance log-softmax + nn.CTCLoss(zero_infinity=True) against targets 1..K_b, and its backward.

@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 
 #include "ptx.cuh"
+#include "lstm_cluster.cuh"
 
 namespace rb {
 
@@ -713,6 +714,8 @@ extern "C" int radtts_lstm_forward(const float* gx, const float* whh, const int*
   RB_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)4 * 32 * round_up(H, 16) * sizeof(float), st));
   RB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
   if (lstm_mma_ok(H, precision)) {
+    // first choice: one thread-block cluster per (direction, 16-utterance slice), exchange through DSMEM (lstm_cluster.cuh)
+    if (lstm_cluster_forward(gx, whh, lens, T, B, H, h_all, gates_save, c_save, lstm_split(precision), st) == 0) return 0;
     d.U = 8;
     d.G = H / 8;
     const int KS = (H + 15) / 16;
@@ -764,6 +767,8 @@ extern "C" int radtts_lstm_backward(const float* dh_all, const float* whh, const
   RB_CUDA(cudaMemsetAsync(dgbuf, 0, (size_t)16 * 32 * round_up(H, 16) * sizeof(float), st));
   RB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
   if (lstm_mma_ok(H, precision)) {
+    if (lstm_cluster_backward(dh_all, whh, lens, gates_save, c_save, T, B, H, dgates_all, lstm_split(precision), st) == 0)
+      return 0;
     d.U = 8;
     d.G = H / 8;
     const int KS = 4 * H / 16;
@@ -797,4 +802,11 @@ extern "C" int radtts_lstm_backward(const float* dh_all, const float* whh, const
                   (void*)&dgates_all, (void*)&dgbuf, (void*)&counters};
   RB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_bwd_kernel, dim3(2 * d.G), dim3(kLstmThreads), args, smem, st));
   return after_launch();
+}
+
+extern "C" int radtts_lstm_debug_timeline(unsigned long long* out16_host) {
+  if (!out16_host) return RADTTS_ERR_INVALID_ARG;
+  RB_CUDA(cudaDeviceSynchronize());
+  RB_CUDA(cudaMemcpyFromSymbol(out16_host, g_cl_dbg, 16 * sizeof(unsigned long long)));
+  return 0;
 }
