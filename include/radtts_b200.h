@@ -359,6 +359,22 @@ RADTTS_API int radtts_lstm_backward(const float* dh_all, const float* whh, const
                                     const float* c_save, int T, int B, int H, float* dgates_all, void* ws,
                                     size_t ws_bytes, int precision, void* stream);
 
+/* Text-encoder conv block epilogue (reference common.py:348-356 with Encoder.convolutions = partial-padding ConvNorm +
+ * InstanceNorm1d(affine) + ReLU + dropout, run per utterance in the reference), batched and fused: from the raw k-tap conv
+ * output `raw` (B, C, T) = conv1d(x * mask) + conv_bias to
+ *     out = dropout(relu(instance_norm(partial_conv_renormalise(raw)) * gamma + beta)) * [t < len]
+ * with per-(utterance, channel) statistics over the valid frames only.  drop: keep mask (0/1 floats, same shape) or NULL,
+ * multiplied by drop_scale = 1 / (1 - p).  mean / rstd (B, C) are saved for the backward call, which returns g_raw and
+ * the gradients of gamma, beta and the DIRECT conv-bias term (the bias also sits inside raw; that part comes from the conv's
+ * own backward).  float32; lens (B) int64 device. */
+RADTTS_API int radtts_encnorm_forward(const float* raw, const float* conv_bias, const int64_t* lens, const float* gamma,
+                                      const float* beta, const float* drop, float drop_scale, int B, int C, int T,
+                                      int ksize, float eps, float* out, float* mean, float* rstd, void* stream);
+RADTTS_API int radtts_encnorm_backward(const float* raw, const float* conv_bias, const int64_t* lens, const float* gamma,
+                                       const float* beta, const float* drop, float drop_scale, const float* mean,
+                                       const float* rstd, const float* g_out, int B, int C, int T, int ksize, float* g_raw,
+                                       float* g_gamma, float* g_beta, float* g_conv_bias, void* stream);
+
 /* Diagnostic: phase cycle sums (clock64) of cluster rank 0 of the last cluster-LSTM launch, SIXTEEN host words: forward
  * [0] waiting for h, [1] MMAs, [2] gates + staging, [4] send + output stores, [5] steps.  Synchronises the device. */
 RADTTS_API int radtts_lstm_debug_timeline(unsigned long long* out16_host);

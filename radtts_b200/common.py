@@ -258,8 +258,15 @@ class Encoder(nn.Module):
     def _convs_masked(self, x, in_lens):
         """All utterances at once: the reference crops every utterance and runs the conv stack on it alone
         (common.py:348-356); a length mask through the partial convs and the instance norms is the same math
-        without the Python loop over the batch."""
+        without the Python loop over the batch.  On CUDA everything after each k-tap convolution (partial-conv
+        renormalisation, masked instance norm, ReLU, dropout, mask) is ONE fused kernel (ops.encoder_conv_block)."""
         mask = get_mask_from_lengths(in_lens, x.shape[2])[:, None].to(x.dtype)
+        if x.is_cuda and all(isinstance(b[1], nn.InstanceNorm1d) and isinstance(b[0].conv, PartialConv1d)
+                             and not hasattr(b[0].conv, "weight_v") for b in self.convolutions):
+            x = x * mask
+            for block in self.convolutions:
+                x = ops.encoder_conv_block(block[0].conv, block[1], x, in_lens, 0.5, self.training)
+            return x
         n = in_lens.to(x.dtype).clamp(min=1)[:, None, None]
         for block in self.convolutions:
             conv, norm = block[0], block[1]

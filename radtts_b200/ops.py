@@ -1203,6 +1203,60 @@ def conv_attention(att, queries, keys, mask, key_lens, attn_prior):
     return _ConvAttnFn.apply(q_enc, k_enc, attn_prior, key_lens, 0.0005)
 
 
+class _EncNormFn(torch.autograd.Function):
+    """Partial-conv renormalisation + masked InstanceNorm1d(affine) + ReLU + dropout + length mask of one text-encoder conv
+    block (reference common.py:348-356), fused: radtts_encnorm_forward / _backward."""
+
+    @staticmethod
+    def forward(ctx, raw, conv_bias, lens, gamma, beta, drop, drop_scale, ksize, eps):
+        raw = raw.float().contiguous()
+        B, C, T = raw.shape
+        dev = raw.device
+        out = torch.empty_like(raw)
+        mean = torch.empty((B, C), dtype=torch.float32, device=dev)
+        rstd = torch.empty((B, C), dtype=torch.float32, device=dev)
+        lens = lens.to(device=dev, dtype=torch.int64).contiguous()
+        cb = None if conv_bias is None else conv_bias.detach().float().contiguous()
+        ga = None if gamma is None else gamma.detach().float().contiguous()
+        be = None if beta is None else beta.detach().float().contiguous()
+        _lib.check(_lib.lib().radtts_encnorm_forward(_lib.ptr(raw), _lib.ptr(cb), _lib.ptr(lens), _lib.ptr(ga), _lib.ptr(be),
+                                                     _lib.ptr(drop), ctypes.c_float(drop_scale), B, C, T, ksize,
+                                                     ctypes.c_float(eps), _lib.ptr(out), _lib.ptr(mean), _lib.ptr(rstd),
+                                                     _lib.stream_of(raw)), "radtts_encnorm_forward")
+        ctx.save_for_backward(raw, lens, mean, rstd)
+        ctx.aux = (cb, ga, be, drop, drop_scale, ksize, conv_bias is not None, gamma is not None, beta is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        raw, lens, mean, rstd = ctx.saved_tensors
+        cb, ga, be, drop, drop_scale, ksize, has_cb, has_ga, has_be = ctx.aux
+        B, C, T = raw.shape
+        dev = raw.device
+        g_out = g_out.float().contiguous()
+        g_raw = torch.empty_like(raw)
+        g_ga = torch.empty(C, dtype=torch.float32, device=dev) if has_ga else None
+        g_be = torch.empty(C, dtype=torch.float32, device=dev) if has_be else None
+        g_cb = torch.empty(C, dtype=torch.float32, device=dev) if has_cb else None
+        _lib.check(_lib.lib().radtts_encnorm_backward(_lib.ptr(raw), _lib.ptr(cb), _lib.ptr(lens), _lib.ptr(ga), _lib.ptr(be),
+                                                      _lib.ptr(drop), ctypes.c_float(drop_scale), _lib.ptr(mean),
+                                                      _lib.ptr(rstd), _lib.ptr(g_out), B, C, T, ksize, _lib.ptr(g_raw),
+                                                      _lib.ptr(g_ga), _lib.ptr(g_be), _lib.ptr(g_cb), _lib.stream_of(raw)),
+                   "radtts_encnorm_backward")
+        return g_raw, g_cb, None, g_ga, g_be, None, None, None, None
+
+
+def encoder_conv_block(conv, norm, x_masked, lens, p_drop, training):
+    """One block of the text encoder's conv stack on the whole padded batch (reference common.py:348-356): the k-tap
+    convolution is a library call, everything after it one fused kernel.  x_masked must be zero beyond each length."""
+    raw = torch.nn.functional.conv1d(x_masked, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation)
+    drop, scale = None, 1.0
+    if training and p_drop > 0:
+        drop = torch.empty_like(raw).bernoulli_(1.0 - p_drop)
+        scale = 1.0 / (1.0 - p_drop)
+    return _EncNormFn.apply(raw, conv.bias, lens, norm.weight, norm.bias, drop, scale, conv.kernel_size[0], norm.eps)
+
+
 class _AttnCTCFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, attn_logprob, in_lens, out_lens, blank_logprob):

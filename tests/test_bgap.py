@@ -159,6 +159,7 @@ def test_conv_stack_forward_and_backward_match_torch(partial, prec, cuda_lib):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             ya = _torch_simple_conv_net(net, xa, lens)
         (ya.float() * g).sum().backward()
+        lib16 = {n: p.grad.clone() for n, p in net.named_parameters()}
         net.zero_grad()
         ops.set_precision(prec)
         xg = x.clone().requires_grad_(True)
@@ -175,7 +176,9 @@ def test_conv_stack_forward_and_backward_match_torch(partial, prec, cuda_lib):
     assert rel(xg.grad, want_x) < tol_x, (rel(xg.grad, want_x), rel(xa.grad, want_x))
     for n, p in net.named_parameters():
         assert p.grad is not None, n
-        assert rel(p.grad, want[n]) < tol, (n, rel(p.grad, want[n]))
+        # same yardstick for the weight gradients of the early layers (their dy went through the later bf16 layers)
+        tol_n = tol if prec == "fp32" else max(tol, 1.5 * rel(lib16[n], want[n]))
+        assert rel(p.grad, want[n]) < tol_n, (n, rel(p.grad, want[n]), rel(lib16[n], want[n]))
 
 
 @pytest.mark.gpu

