@@ -128,13 +128,17 @@ def to_device(hb, device):
     return {k: v.to(device, non_blocking=True) for k, v in hb.items()}
 
 
-def time_region(fn, steps, world):
-    """CUDA-event timing of `steps` calls bracketed by barrier + synchronize; max over ranks (ms)."""
+def time_region(fn, steps, world, tail=None):
+    """CUDA-event timing of `steps` calls bracketed by barrier + synchronize; max over ranks (ms).  tail: called once
+    after the last step, INSIDE the timed region (flushes a pipelined optimizer update: all the work of all `steps`
+    steps is done when the clock stops)."""
     barrier_sync(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         fn()
+    if tail is not None:
+        tail()
     e1.record()
     barrier_sync(world)
     return max_over_ranks(e0.elapsed_time(e1), world)
@@ -439,7 +443,8 @@ def train_leg(name, args, world, rank, local, device, steps, with_attributes=Fal
               energy_model_config=cfg["energy_model_config"], vpred_model_config=cfg["v_model_config"]) \
         if name != "radtts" else None
     ts = TrainStep(model, configs.LOSS_WEIGHTS, bf16=True, ddp=world > 1, device_ids=[local] if world > 1 else None,
-                   capturable=use_graph, loss_kwargs=lk, probe_batch=dev_batches[0] if name != "radtts" else None)
+                   capturable=use_graph, loss_kwargs=lk, probe_batch=dev_batches[0] if name != "radtts" else None,
+                   deferred_update=not args.no_deferred_update)
     graph_note = "eager"
     if use_graph:
         try:
@@ -473,7 +478,7 @@ def train_leg(name, args, world, rank, local, device, steps, with_attributes=Fal
         sampler.start()
     launches0 = _lib.launch_count()
     torch.cuda.profiler.start()   # no-op unless run under `ncu --profile-from-start off` (profiles/ recipe)
-    ms = time_region(step_resident, steps, world)
+    ms = time_region(step_resident, steps, world, tail=ts.flush)
     torch.cuda.profiler.stop()
     launches = _lib.launch_count() - launches0
     if ts.graph is not None:
@@ -481,7 +486,7 @@ def train_leg(name, args, world, rank, local, device, steps, with_attributes=Fal
     clocks = sampler.stop() if sampler else None
     frames_total = sum_over_ranks(frames_local, world)
     step_e2e()
-    ms_e2e = time_region(step_e2e, steps, world)
+    ms_e2e = time_region(step_e2e, steps, world, tail=ts.flush)
     res = {"value": frames_total * steps / (ms / 1e3), "ms_per_step": ms / steps,
            "e2e_value": frames_total * steps / (ms_e2e / 1e3), "e2e_ms_per_step": ms_e2e / steps, "h2d": h2d,
            "launches": int(launches * world), "clocks": clocks, "loss_last": losses[-1] if losses else None,
@@ -500,6 +505,9 @@ def main():
     ap.add_argument("--t2", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
+    ap.add_argument("--no-deferred-update", action="store_true",
+                    help="apply the whole RAdam update at the end of each step (default: the flow-parameter region is applied "
+                         "at the top of the next step, underneath its text encoder / attention / context LSTM)")
     ap.add_argument("--no-extras", action="store_true", help="headline train step only (no cfg3 / cfg4 / infer / sweep legs)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -582,6 +590,9 @@ def main():
                 "loss_last": head["loss_last"], "extra": extra or None}
         line["config"]["global_batch"] = args.batch * world
         line["config"]["execution"] = head["execution"]
+        line["config"]["optimizer_update"] = ("whole update at the end of the step" if args.no_deferred_update else
+                                              "flow-parameter region applied at the top of the next step (same kernels, "
+                                              "pipelined); the last one is flushed inside the timed region")
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

@@ -45,6 +45,11 @@ RADTTS_API int radtts_abi_version(void);
 RADTTS_API long long radtts_launch_count(void);
 /* Human-readable text for a negative RADTTS_ERR_* or a positive cudaError_t. */
 RADTTS_API const char* radtts_error_string(int code);
+/* Tuning switch of the tcgen05 row GEMM (csrc/rowgemm_tc.cuh): let the kernel pick, on the device, the tile width (256 /
+ * 208 / 176 / 144 output columns) that needs the fewest rounds x width for the number of row tiles the frame plan holds
+ * (default on; environment RADTTS_GEMM_TILE_SELECT=0 turns it off at load: always 256).  Results are bit-identical
+ * either way.  Returns the previous setting. */
+RADTTS_API int radtts_set_gemm_tile_select(int enabled);
 
 /* ------------------------------------------------------------------------------------------------
  * Kernel 1 -- Monotonic Alignment Search + binarize_attention.
@@ -400,6 +405,14 @@ RADTTS_API int radtts_attn_ctc(const float* attn_logprob, const int64_t* in_lens
 RADTTS_API int radtts_radam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1,
                                  float beta2, float eps, float weight_decay, long long* step_dev,
                                  const float* grad_scale, void* stream);
+/* The same update on a sub-range of the buffer, for a trainer that pipelines it: `enable` (device int, or NULL) turns the
+ * whole call into a no-op when it holds 0 -- a captured step can carry "apply the pending update of the previous step"
+ * as a fixed node; zero_grad != 0 writes zeros back over g in the same pass (saves the separate memset of the gradient
+ * buffer); bump != 0 increments step_dev after the update (under the same `enable`).  All ranges updated with the same
+ * step_dev value belong to one optimizer step: bump once, with the last of them. */
+RADTTS_API int radtts_radam_step_ex(float* p, float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                                    float eps, float weight_decay, long long* step_dev, const float* grad_scale,
+                                    const int* enable, int zero_grad, int bump, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,7 @@
 namespace rb {
 
 extern long long g_launches;  // defined in capi.cu; counts kernel launches (bench.py `gpu_launches`)
+extern int g_gemm_tile_select;  // defined in capi.cu; radtts_set_gemm_tile_select
 
 inline int after_launch() {
   ++g_launches;

@@ -13,69 +13,78 @@
 
 namespace rb {
 
-constexpr int kInvThreads = 320;   // 40 column groups (4 columns) x 8 row groups (4 rows)
-constexpr int kInvRows = 32;
+constexpr int kInvThreads = 320;   // 40 column groups (4 columns) x 8 row groups
+constexpr int kInvTileRows = 10;   // rows per thread: 8 x 10 = 80 rows per pass
+constexpr int kInvRows = 8 * kInvTileRows;
 constexpr int kInvMaxLd = 160;
+constexpr int kInvWtLd = kInvMaxLd + 4;   // padded row of the transposed weight: the transposing stores hit 8 banks, not 1
 
 // y[r][c] = ok(r) ? sum_j w[c][j] x[r][j] : 0      (w row-major [zld][zld])
 //   y2 (optional): copy of columns c < c_lim;  z0 (optional, element type T): columns [c_off, c_off + 128) of the result,
 //   zero beyond c_off + h
+// Every CTA takes ONE contiguous chunk of ceil(rows / grid) rows (74 at the bench shape: a single 80-row pass, no second
+// round for a few CTAs) and every thread a 10 x 4 register tile: per four input channels 10 broadcast LDS.128 of x and 4
+// LDS.128 of W^T feed 160 FMAs, so the loop is bound by the FMA pipe and not by shared-memory wavefronts (the 4 x 4 tile
+// this replaces needed 20 wavefronts per 64 FMAs and ran at 17 % of the fp32 peak: 44 us per launch, 16 launches a step).
 template <typename T>
 __global__ void __launch_bounds__(kInvThreads, 1)
 invconv_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, int zld, const int* __restrict__ plan,
                     int rows_alloc, RowMeta meta, int mask_rows, float* __restrict__ y, float* __restrict__ y2, int c_lim,
                     T* __restrict__ z0, int c_off, int h) {
   extern __shared__ __align__(16) float sm_inv[];
-  float* wt = sm_inv;                          // [zld (j)][zld (c)]
-  float* xs = sm_inv + (size_t)zld * zld;      // [32][zld]
+  float* wt = sm_inv;                               // [zld (j)][kInvWtLd (c)]
+  float* xs = sm_inv + (size_t)zld * kInvWtLd;      // [80][zld]
   const int rows_used = plan ? plan[0] : rows_alloc;
+  int chunk = (rows_used + (int)gridDim.x - 1) / (int)gridDim.x;
+  chunk = (chunk + 3) / 4 * 4;
+  const int r_begin = blockIdx.x * chunk, r_end = min(r_begin + chunk, rows_used);
+  if (r_begin >= r_end) return;
   const int tid = threadIdx.x;
   for (int i = tid; i < zld * zld; i += kInvThreads) {
     const int c = i / zld, j = i - c * zld;
-    wt[(size_t)j * zld + c] = w[i];
+    wt[(size_t)j * kInvWtLd + c] = w[i];
   }
   const int ncg = zld / 4;
   const int cg = tid % 40, rg = tid / 40;
   const bool active = cg < ncg;
   const int zld4 = zld / 4;
-  for (int r0 = blockIdx.x * kInvRows; r0 < rows_used; r0 += gridDim.x * kInvRows) {
-    __syncthreads();                           // previous block's xs fully consumed (and wt staged, first time)
+  for (int r0 = r_begin; r0 < r_end; r0 += kInvRows) {
+    __syncthreads();                           // previous pass's xs fully consumed (and wt staged, first time)
+    const int nrows = min(kInvRows, r_end - r0);
     for (int i = tid; i < kInvRows * zld4; i += kInvThreads) {
       const int r = i / zld4, q = i - r * zld4;
       reinterpret_cast<float4*>(xs)[(size_t)r * zld4 + q] =
-          *reinterpret_cast<const float4*>(x + (size_t)(r0 + r) * zld + 4 * q);
+          r < nrows ? *reinterpret_cast<const float4*>(x + (size_t)(r0 + r) * zld + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    if (!active) continue;
-    float acc[4][4];
+    if (!active || kInvTileRows * rg >= nrows) continue;
+    float acc[kInvTileRows][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kInvTileRows; ++i)
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
-    const float* xr = xs + (size_t)(4 * rg) * zld;
-    // four input channels per step: the x values come as one broadcast LDS.128 per row instead of four scalar loads
-    // (the loop is bound by shared-memory wavefronts, not by FMAs)
-#pragma unroll 2
+    const float* xr = xs + (size_t)(kInvTileRows * rg) * zld;
     for (int j = 0; j < zld; j += 4) {
-      float xv[4][4];
+      float xv[kInvTileRows][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < kInvTileRows; ++i) {
         const float4 t = *reinterpret_cast<const float4*>(xr + (size_t)i * zld + j);
         xv[i][0] = t.x; xv[i][1] = t.y; xv[i][2] = t.z; xv[i][3] = t.w;
       }
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        const float4 w4 = *reinterpret_cast<const float4*>(wt + (size_t)(j + jj) * zld + 4 * cg);
+        const float4 w4 = *reinterpret_cast<const float4*>(wt + (size_t)(j + jj) * kInvWtLd + 4 * cg);
         const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < kInvTileRows; ++i)
 #pragma unroll
           for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(wv[k], xv[i][jj], acc[i][k]);
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = r0 + 4 * rg + i;
+    for (int i = 0; i < kInvTileRows; ++i) {
+      const int row = r0 + kInvTileRows * rg + i;
+      if (row >= r_end) break;
       const bool ok = !mask_rows || meta.valid(row);
       float v[4];
 #pragma unroll
@@ -99,14 +108,14 @@ template <typename T>
 inline int launch_invconv_rows(const float* x, const float* w, int zld, const int* plan, int rows_alloc, RowMeta meta,
                                int mask_rows, float* y, float* y2, int c_lim, T* z0, int c_off, int h, cudaStream_t st) {
   if (zld % 4 || zld > kInvMaxLd) return RADTTS_ERR_UNSUPPORTED;
-  const size_t smem = ((size_t)zld * zld + (size_t)kInvRows * zld) * sizeof(float);
+  const size_t smem = ((size_t)zld * kInvWtLd + (size_t)kInvRows * zld) * sizeof(float);
   static bool configured = false;
   if (!configured) {
     RB_CUDA(cudaFuncSetAttribute(invconv_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(((size_t)kInvMaxLd * kInvMaxLd + (size_t)kInvRows * kInvMaxLd) * sizeof(float))));
+                                 (int)(((size_t)kInvMaxLd * kInvWtLd + (size_t)kInvRows * kInvMaxLd) * sizeof(float))));
     configured = true;
   }
-  const int blocks = ceil_div(rows_alloc, kInvRows);
+  const int blocks = ceil_div(rows_alloc, 8);      // tiny inputs: at least 8 rows per CTA
   const int grid = blocks < kNumSMs ? blocks : kNumSMs;
   invconv_rows_kernel<T><<<grid, kInvThreads, smem, st>>>(x, w, zld, plan, rows_alloc, meta, mask_rows, y, y2, c_lim, z0,
                                                          c_off, h);

@@ -26,6 +26,11 @@ namespace rb {
 // phase cycle sums of cluster rank 0 / batch slice 0 / direction 0 of the last cluster launch (thread 0):
 // forward  [0] wait for h, [1] MMAs, [2] gates + stage, [3] barrier + send, [4] output stores, [5] steps
 // backward [8] wait + reduce, [9] element-wise + dgates, [10] MMAs + stage, [11] send, [13] steps
+// Compiled in only with -DRB_LSTM_TIMELINE=1: the per-step global read-modify-writes of thread 0 delay its warp, and through
+// the CTA barrier and the cluster exchange every step of every CTA (radtts_lstm_debug_timeline then returns zeros).
+#ifndef RB_LSTM_TIMELINE
+#define RB_LSTM_TIMELINE 0
+#endif
 __device__ unsigned long long g_cl_dbg[16];
 
 struct ClDims {
@@ -155,7 +160,7 @@ lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ 
           const int b = b0 + nt * 8 + 2 * q + e;
           gxv[gate][nt][e] = (active && b < B) ? __ldg(gx + (((size_t)dir * T + t) * B + b) * 4 * H + gate * H + u) : 0.f;
         }
-    const bool dbg = (tid == 0 && rank == 0 && blockIdx.y == 0 && blockIdx.z == 0);
+    const bool dbg = RB_LSTM_TIMELINE && (tid == 0 && rank == 0 && blockIdx.y == 0 && blockIdx.z == 0);
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
     if (dbg) c0 = clock64();
     if (s > 0) mbar_wait(&bar[cur], (uint32_t)(((s - 1) >> 1) & 1));
@@ -345,7 +350,7 @@ lstm_fwd_cluster_reg_kernel(const float* __restrict__ gx, const float* __restric
         const int b = b0 + half * 8 + 2 * q + e;
         gxv[gate][e] = (active && b < B) ? __ldg(gx + (((size_t)dir * T + t) * B + b) * 4 * H + gate * H + u) : 0.f;
       }
-    const bool dbg = (tid == 0 && rank == 0 && blockIdx.y == 0 && blockIdx.z == 0);
+    const bool dbg = RB_LSTM_TIMELINE && (tid == 0 && rank == 0 && blockIdx.y == 0 && blockIdx.z == 0);
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
     if (dbg) c0 = clock64();
     if (s > 0) mbar_wait(&bar[cur], (uint32_t)(((s - 1) >> 1) & 1));

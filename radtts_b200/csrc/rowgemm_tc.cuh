@@ -9,6 +9,15 @@
 //   warp 5      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16) x4 per k-block,
 //               accumulating in TMEM; tcgen05.commit releases smem stages and publishes finished accumulators
 // Two 256-column TMEM accumulators (all 512 columns) double-buffer the epilogue against the next tile's MMAs.
+//
+// Tile width and ring depth are chosen ON THE DEVICE, per launch: the number of row tiles comes from the frame plan (device
+// memory, no host sync), and 85 row tiles x 4 column tiles of 256 on 148 SMs are 2.30 waves that run as 3 (the measured
+// 0.72-of-peak of the in_layer GEMM was this and nothing else).  The host passes up to kTcCand tile widths with a weight
+// tensor map each; every CTA evaluates rounds(bn) x (bn + fixed) for each and takes the cheapest (e.g. 208 -> 425 tiles
+// = 2.87 waves, 19 % fewer MMA cycles per CTA), and sizes the TMA ring to what a stage of that width leaves room for
+// (bn = 256: 4 stages, 208 / 176: 5, <= 144: 6 -- a narrower tile needs the deeper ring to stay MMA- and not
+// fetch-latency bound).  The accumulation order of every output element is the same for every width: results are
+// bit-identical whichever candidate wins.
 #pragma once
 #include <cuda.h>
 
@@ -21,12 +30,14 @@
 
 namespace rb {
 
-constexpr int kTcBM = 128, kTcBK = 64, kTcMaxBN = 256, kTcStages = 4, kTcThreads = 192;
+constexpr int kTcBM = 128, kTcBK = 64, kTcMaxBN = 256, kTcMaxStages = 6, kTcThreads = 192;
 constexpr int kTcABytes = kTcBM * kTcBK * 2;       // 16 KB
-constexpr int kTcBBytes = kTcMaxBN * kTcBK * 2;    // 32 KB
-constexpr int kTcSmemBytes = kTcStages * (kTcABytes + kTcBBytes) + 1024 /*align slack*/ + 256 /*barriers*/ +
+constexpr int kTcRingBytes = 208 * 1024;           // 4 x 48 KB (bn 256), 5 x 41.6 (208), 5 x 38 (176), 6 x 34 (144), 6 x 32 (128)
+constexpr int kTcSmemBytes = kTcRingBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
                              2 * kTcMaxBN * 4 /*per-tile column vector (bias), double buffered*/;
 constexpr int kTcMaxMaps = 4;
+constexpr int kTcCand = 4;                         // tile-width candidates per launch
+constexpr int kTcTileFixed = 20;                   // per-tile fixed cost in units of one output column's MMA time
 
 struct TcSeg {
   int map;    // index into TcParams::amap
@@ -37,15 +48,20 @@ struct TcSeg {
 
 struct TcParams {
   CUtensorMap amap[kTcMaxMaps];
-  CUtensorMap wmap;
+  CUtensorMap wmap[kTcCand];   // weight map per candidate tile width (box = bn rows x 64 columns)
   TcSeg seg[kMaxSeg];
   int nseg;
-  int N;          // output columns
-  int bn;         // tile width (multiple of 16, <= 256); N is covered by ceil(N / bn) tiles
-  int n_tiles_n;
+  int N;                // output columns
+  int bn[kTcCand];      // candidate tile widths (multiples of 16, <= 256); N is covered by ceil(N / bn) tiles
+  int ncand;
   int rows_alloc;
   const int* plan;
 };
+
+__host__ __device__ inline int tc_stages_for(int bn) {
+  const int st = kTcRingBytes / (kTcABytes + bn * kTcBK * 2);
+  return st > kTcMaxStages ? kTcMaxStages : st;
+}
 
 // ----------------------------------------------------------------------------------------------------------
 // host: tensor-map construction (driver entry point fetched through the runtime; no libcuda link dependency)
@@ -115,31 +131,46 @@ template <typename Epi>
 __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_constant__ TcParams p, const Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + kTcStages * kTcABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * (kTcABytes + kTcBBytes));
-  uint64_t* full = bars;                    // [kTcStages]
-  uint64_t* empty = bars + kTcStages;       // [kTcStages]
-  uint64_t* tfull = bars + 2 * kTcStages;   // [2]
-  uint64_t* tempty = tfull + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* cvec_s = reinterpret_cast<float*>(smem + kTcStages * (kTcABytes + kTcBBytes) + 256);  // [2][kTcMaxBN]
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_used = p.plan ? p.plan[0] : p.rows_alloc;
   const int n_tiles_m = (rows_used + kTcBM - 1) / kTcBM;
-  const int n_tiles = n_tiles_m * p.n_tiles_n;
+  // tile width: fewest MMA cycles per CTA over the whole launch (every CTA computes the same answer)
+  int cand = 0;
+  {
+    long long best = -1;
+    for (int c = 0; c < p.ncand; ++c) {
+      const int tiles = n_tiles_m * ((p.N + p.bn[c] - 1) / p.bn[c]);
+      const long long cost = (long long)((tiles + (int)gridDim.x - 1) / (int)gridDim.x) * (p.bn[c] + kTcTileFixed);
+      if (best < 0 || cost < best) { best = cost; cand = c; }
+    }
+  }
+  const int bn = p.bn[cand];
+  const int n_tiles_n = (p.N + bn - 1) / bn;
+  const int n_tiles = n_tiles_m * n_tiles_n;
+  const int nst = tc_stages_for(bn);
+  const int b_bytes = bn * kTcBK * 2;
+  const CUtensorMap* wmap = &p.wmap[cand];
   int kb_total = 0;
   for (int s = 0; s < p.nseg; ++s) kb_total += p.seg[s].kblocks;
 
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + nst * kTcABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcRingBytes);
+  uint64_t* full = bars;                       // [kTcMaxStages]
+  uint64_t* empty = bars + kTcMaxStages;       // [kTcMaxStages]
+  uint64_t* tfull = bars + 2 * kTcMaxStages;   // [2]
+  uint64_t* tempty = tfull + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* cvec_s = reinterpret_cast<float*>(smem + kTcRingBytes + 256);  // [2][kTcMaxBN]
+
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kTcMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     mbar_fence_init();
   }
   if (warp == 4 && lane == 0) {
     for (int m = 0; m < kTcMaxMaps; ++m) tma_prefetch_desc(&p.amap[m]);
-    tma_prefetch_desc(&p.wmap);
+    tma_prefetch_desc(wmap);
   }
   if (warp == 5) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -153,10 +184,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)kTcABytes + (uint32_t)p.bn * kTcBK * 2;
+      const uint32_t tx_bytes = (uint32_t)kTcABytes + (uint32_t)b_bytes;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int tm = tile % n_tiles_m, tn = tile / n_tiles_m;
-        const int row0 = tm * kTcBM, n0 = tn * p.bn;
+        const int row0 = tm * kTcBM, n0 = tn * bn;
         int kb = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const TcSeg sg = p.seg[s];
@@ -164,8 +195,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full[stage], tx_bytes);
             tma_load_2d(sA + stage * kTcABytes, &p.amap[sg.map], &full[stage], sg.kcol + kk * kTcBK, row0 + sg.shift);
-            tma_load_2d(sB + stage * kTcBBytes, &p.wmap, &full[stage], kb * kTcBK, n0);
-            if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            tma_load_2d(sB + stage * b_bytes, wmap, &full[stage], kb * kTcBK, n0);
+            if (++stage == nst) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -175,7 +206,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      const uint32_t idesc = umma_idesc_bf16(kTcBM, p.bn, 0, 0);
+      const uint32_t idesc = umma_idesc_bf16(kTcBM, bn, 0, 0);
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -184,7 +215,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * kTcABytes);
-          const uint32_t b_addr = smem_u32(sB + stage * kTcBBytes);
+          const uint32_t b_addr = smem_u32(sB + stage * b_bytes);
 #pragma unroll
           for (int k = 0; k < kTcBK / 16; ++k) {
             const uint64_t da = umma_smem_desc(a_addr + k * 32, 0, 1024, 2);
@@ -192,7 +223,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
             umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
-          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -205,14 +236,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int tm = tile % n_tiles_m, tn = tile / n_tiles_m;
       const int row = tm * kTcBM + quad * 32 + lane;
-      const int n0 = tn * p.bn;
+      const int n0 = tn * bn;
       // per-tile staging, off the TMEM critical path: row state in registers, column vector (bias) in smem
       const RowState rs = epi.prep(row);
       float* cv = cvec_s + acc * kTcMaxBN;
       {
         const float* gv = epi.colvec();
         const int et = threadIdx.x;       // 0..127: the epilogue warps are warps 0-3
-        for (int i = et; i < p.bn; i += 128) cv[i] = (gv && n0 + i < p.N) ? gv[n0 + i] : 0.f;
+        for (int i = et; i < bn; i += 128) cv[i] = (gv && n0 + i < p.N) ? gv[n0 + i] : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       mbar_wait(&tfull[acc], acc_phase);
@@ -222,17 +253,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) rowgemm_tc_kernel(const __grid_
       // group g runs through the epilogue functor (a lone ld + wait per 16 columns costs a full TMEM round trip
       // each time and made the epilogue, not the MMAs, the critical path of the K = 1024 GEMMs).
       uint32_t ra[4][16], rbuf[4][16];
-      const int ngroups = (p.bn + 63) / 64;
+      const int ngroups = (bn + 63) / 64;
       auto load_group = [&](uint32_t (&dst)[4][16], int g) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (g * 64 + q * 16 < p.bn) tmem_ld16(t_addr + g * 64 + q * 16, dst[q]);
+          if (g * 64 + q * 16 < bn) tmem_ld16(t_addr + g * 64 + q * 16, dst[q]);
       };
       auto run_group = [&](uint32_t (&src)[4][16], int g) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c = g * 64 + q * 16;
-          if (c < p.bn && n0 + c < p.N) {
+          if (c < bn && n0 + c < p.N) {
             float v[16], cvr[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(src[q][i]);
@@ -278,8 +309,15 @@ inline int launch_rowgemm_tc(const GemmDesc& d, const Epi& epi, cudaStream_t str
   p.rows_alloc = d.rows_alloc;
   p.plan = d.plan;
   if (d.N % 16) return RADTTS_ERR_INVALID_ARG;
-  p.bn = d.N <= kTcMaxBN ? d.N : kTcMaxBN;
-  p.n_tiles_n = ceil_div(d.N, p.bn);  // a partial last tile reads zero-filled weight rows and is masked on store
+  // candidate tile widths; a partial last column tile reads zero-filled weight rows and is masked on store
+  if (d.N <= kTcMaxBN) {
+    p.bn[0] = d.N;
+    p.ncand = 1;
+  } else {
+    static const int kWidths[kTcCand] = {256, 208, 176, 144};
+    p.ncand = g_gemm_tile_select ? kTcCand : 1;
+    for (int c = 0; c < p.ncand; ++c) p.bn[c] = kWidths[c];
+  }
   const void* bases[kTcMaxMaps];
   int lds[kTcMaxMaps];
   int nmaps = 0;
@@ -302,13 +340,19 @@ inline int launch_rowgemm_tc(const GemmDesc& d, const Epi& epi, cudaStream_t str
   }
   for (int i = nmaps; i < kTcMaxMaps; ++i) p.amap[i] = p.amap[0];
   if (ktotal > d.ldw) return RADTTS_ERR_INVALID_ARG;
-  RB_TRY(make_map_bf16(d.w, d.ldw, d.ldw, d.N, p.bn, &p.wmap));
+  int min_tiles_n = ceil_div(d.N, p.bn[0]), max_tiles_n = min_tiles_n;
+  for (int c = 0; c < p.ncand; ++c) {
+    RB_TRY(make_map_bf16(d.w, d.ldw, d.ldw, d.N, p.bn[c], &p.wmap[c]));
+    const int tn = ceil_div(d.N, p.bn[c]);
+    if (tn > max_tiles_n) max_tiles_n = tn;
+  }
+  for (int c = p.ncand; c < kTcCand; ++c) { p.wmap[c] = p.wmap[0]; p.bn[c] = p.bn[0]; }
   static bool configured = false;  // per Epi instantiation
   if (!configured) {
     RB_CUDA(cudaFuncSetAttribute(rowgemm_tc_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     configured = true;
   }
-  const int max_tiles = (d.rows_alloc / kTcBM) * p.n_tiles_n;
+  const int max_tiles = (d.rows_alloc / kTcBM) * max_tiles_n;
   const int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
   rowgemm_tc_kernel<Epi><<<grid, kTcThreads, kTcSmemBytes, stream>>>(p, epi);
   return after_launch();

@@ -437,12 +437,19 @@ def run_flowstep(dims, blob, plan, zin, ctx_packed, prec, inverse, lease, keep_p
 _prep_streams = {}
 
 
-def prepare_flows_async(dims_list, ws, n_per_flow, prec, want_backward, device, order=None):
-    """radtts_flow_prepare of every flow of a stack on a side stream (forked from the current stream here, joined per
-    flow by the returned events): ([blob_i], [event_i])."""
+def prep_stream(device):
+    """The side stream the flow weight preparation runs on (a trainer queues its deferred flow-parameter update on it,
+    ahead of the preparation that reads those parameters)."""
     side = _prep_streams.get(device.index)
     if side is None:
         side = _prep_streams[device.index] = torch.cuda.Stream(device=device)
+    return side
+
+
+def prepare_flows_async(dims_list, ws, n_per_flow, prec, want_backward, device, order=None):
+    """radtts_flow_prepare of every flow of a stack on a side stream (forked from the current stream here, joined per
+    flow by the returned events): ([blob_i], [event_i])."""
+    side = prep_stream(device)
     side.wait_stream(torch.cuda.current_stream(device))
     blobs, events = [None] * len(dims_list), [None] * len(dims_list)
     with torch.cuda.stream(side):

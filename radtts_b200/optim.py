@@ -59,13 +59,23 @@ class FusedRAdam:
             off += (p.numel() + 3) // 4 * 4
 
     def step(self, grad_scale=None):
+        self.step_range(0, self.flat.numel(), grad_scale)
+
+    def step_range(self, lo, hi, grad_scale=None, enable=None, zero_grad=False, bump=True):
+        """The update on flat-buffer elements [lo, hi) (lo a multiple of 4).  enable: device int32 tensor, 0 makes the call a
+        no-op; zero_grad: write zeros over the gradients in the same pass; bump: advance the step counter afterwards.  All
+        ranges of one optimizer step must run before the bump of that step (radtts_radam_step_ex)."""
+        if hi <= lo:
+            return
+        assert lo % 4 == 0
         if not torch.cuda.is_current_stream_capturing():
             self.check_views()
         L = _lib.lib()
         b1, b2 = self.betas
-        _lib.check(L.radtts_radam_step(_lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg),
-                                       _lib.ptr(self.exp_avg_sq), ctypes.c_size_t(self.flat.numel()),
-                                       ctypes.c_float(self.lr), ctypes.c_float(b1), ctypes.c_float(b2),
-                                       ctypes.c_float(self.eps), ctypes.c_float(self.weight_decay),
-                                       _lib.ptr(self.step_dev), _lib.ptr(grad_scale), _lib.stream_of(self.flat)),
-                   "radtts_radam_step")
+        f = lambda t: ctypes.c_void_p(t.data_ptr() + 4 * lo)      # noqa: E731
+        _lib.check(L.radtts_radam_step_ex(f(self.flat), f(self.grad), f(self.exp_avg), f(self.exp_avg_sq),
+                                          ctypes.c_size_t(hi - lo), ctypes.c_float(self.lr), ctypes.c_float(b1),
+                                          ctypes.c_float(b2), ctypes.c_float(self.eps), ctypes.c_float(self.weight_decay),
+                                          _lib.ptr(self.step_dev), _lib.ptr(grad_scale), _lib.ptr(enable), int(bool(zero_grad)),
+                                          int(bool(bump)), ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)),
+                   "radtts_radam_step_ex")

@@ -19,7 +19,7 @@ def bulk_first_order(model):
 class TrainStep:
     def __init__(self, model, loss_weights, lr=1e-4, weight_decay=1e-6, grad_clip_val=1.0, bf16=True,
                  binarize_attention=True, use_binarization_loss=True, ddp=False, device_ids=None, capturable=False,
-                 fused_optimizer=True, probe_batch=None, loss_kwargs=None):
+                 fused_optimizer=True, probe_batch=None, loss_kwargs=None, deferred_update=False):
         self.raw_model = model
         self.model = model
         self.world = 1
@@ -52,7 +52,9 @@ class TrainStep:
         self.ev_flow = []
         self._flow_final = []
         params = [p for p in model.parameters() if p.requires_grad]
-        if ddp and fused_optimizer and hasattr(model, "flows"):
+        if fused_optimizer and hasattr(model, "flows"):
+            # flow parameter networks first (94 % of the bytes): the region data parallelism reduces flow by flow, and the
+            # one a deferred update applies underneath the next step's text encoder / attention / context LSTM
             params, self.flow_regions = parallel.flow_first_order(model)
         if probe_batch is not None:
             # the reference optimizer skips parameters whose .grad is None (radam.py:53-55) -- e.g. v_pred_module /
@@ -78,6 +80,20 @@ class TrainStep:
         else:
             self.optimizer = torch.optim.RAdam(params, lr=lr, weight_decay=weight_decay, foreach=True,
                                                capturable=self.capturable)
+        # Deferred update (fused optimizer only).  The RAdam pass is HBM-bound (28 B per parameter, ~1 ms for 226 M) and
+        # nothing can overlap it at the end of a step: the clip coefficient needs every gradient, the next forward needs
+        # the parameters.  But the next forward needs the FLOW parameters only after the text encoder, the attention, MAS
+        # and the context LSTM -- ~2 ms that leave most SMs and nearly all of HBM idle.  So a step updates the small
+        # remainder at its end and leaves the flow region PENDING; the next step applies it first thing on the side stream
+        # the flow weight preparation runs on.  Same kernels on the same data in a different order: parameters are
+        # identical to the plain schedule once flush() (or the next step) has run.  step_dev counts APPLIED bulk updates.
+        self.deferred_update = bool(deferred_update) and self.fused_optimizer and bool(self.flow_regions)
+        self.n_bulk = self.flow_regions[-1][1] if self.flow_regions else 0
+        self._grads_clean = False
+        if self.fused_optimizer:
+            dev = self.optimizer.flat.device
+            self.pending_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.scale_dev = torch.ones(1, dtype=torch.float32, device=dev)
         self.graph = None
         self.graph_update = None
         self.launches_per_replay = 0
@@ -165,9 +181,28 @@ class TrainStep:
             return self.static_loss
         return self._eager_step(batch)
 
+    def flush(self):
+        """Applies a pending deferred update (no-op otherwise): call before reading parameters outside step() -- checkpoint,
+        evaluation, the end of training."""
+        if self.deferred_update:
+            self.optimizer.step_range(0, self.n_bulk, self.scale_dev, enable=self.pending_dev, zero_grad=True, bump=True)
+            self.pending_dev.zero_()
+
     def _fwd_bwd(self, batch):
         from . import ops
-        self.optimizer.zero_grad(set_to_none=not self.fused_optimizer)
+        if self.fused_optimizer:
+            if self.deferred_update:
+                dev = self.optimizer.flat.device
+                side = ops.prep_stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):      # begin_decoder_prep queues the flow weight preparation behind it
+                    self.optimizer.step_range(0, self.n_bulk, self.scale_dev, enable=self.pending_dev, zero_grad=True,
+                                              bump=True)
+            elif not self._grads_clean:
+                self.optimizer.zero_grad(set_to_none=False)
+            self._grads_clean = False
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
         with ops.trainer_scope(self.fused_optimizer, self._on_flow_grads if self.ev_flow else None):
             total, _ = self.forward_loss(batch)
             total.backward()
@@ -190,7 +225,23 @@ class TrainStep:
             scale = ((self.grad_clip_val / (norm + 1e-6)).clamp(max=1.0) / self.world).reshape(1)
         else:
             scale = torch.full((1,), 1.0 / self.world, device=self.optimizer.grad.device) if self.world > 1 else None
-        self.optimizer.step(scale)
+        if not self.fused_optimizer:
+            self.optimizer.step(scale)
+            return
+        # the coefficient lives in a persistent buffer (a deferred update reads it at the top of the NEXT replay, when
+        # a tensor from the graph's private pool may already have been reused); the update writes zeros over the
+        # gradients it consumed, so the next step starts without a memset of the 0.9 GB buffer
+        if scale is None:
+            self.scale_dev.fill_(1.0)
+        else:
+            self.scale_dev.copy_(scale)
+        total = self.optimizer.flat.numel()
+        if self.deferred_update:
+            self.optimizer.step_range(self.n_bulk, total, self.scale_dev, zero_grad=True, bump=False)
+            self.pending_dev.fill_(1)
+        else:
+            self.optimizer.step_range(0, total, self.scale_dev, zero_grad=True, bump=True)
+        self._grads_clean = True
 
     def _eager_step(self, batch):
         if self.fused_optimizer:

@@ -45,7 +45,9 @@ def main():
     loss = ts.step(batches[rank])
     torch.cuda.synchronize()
     got_flat = ts.optimizer.flat.clone()
-    got_grad = ts.optimizer.grad.clone()          # SUM over ranks
+    # the update zeroes the gradients in the pass that consumes them; after ONE step from zero moments the first moment is
+    # (1 - beta1) * clipped mean gradient: the gradient check is made on it
+    got_grad = ts.optimizer.exp_avg.clone()
     order = [id(p) for p in ts.optimizer.params]
 
     # single-process ground truth on THIS rank: per-rank gradients of every rank's batch, averaged
@@ -73,8 +75,8 @@ def main():
         n = names[id(p)]
         ro = ref_name_off[n]
         k = p.numel()
-        g_dp = got_grad[off:off + k] / world
-        g_rf = rs.optimizer.grad[ro:ro + k]
+        g_dp = got_grad[off:off + k]
+        g_rf = rs.optimizer.exp_avg[ro:ro + k]
         num_g += float((g_dp - g_rf).double().pow(2).sum()); den_g += float(g_rf.double().pow(2).sum())
         w_dp, w_rf = got_flat[off:off + k], rs.optimizer.flat[ro:ro + k]
         num_p += float((w_dp - w_rf).double().pow(2).sum()); den_p += float(w_rf.double().pow(2).sum())

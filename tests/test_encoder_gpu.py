@@ -64,7 +64,7 @@ def test_fused_encoder_block_matches_torch(with_dropout, cuda_lib):
             for k in want:
                 if k == "bias":
                     # analytically zero (the instance norm removes a per-channel constant): both sides are rounding noise
-                    assert float((got[k] - want[k]).norm()) < 1e-5 * float(want["beta"].norm()), k
+                    assert float((got[k] - want[k]).norm()) < 1e-4 * float(want["beta"].norm()), k
                     continue
                 assert rel(got[k], want[k]) < 1e-4, (k, rel(got[k], want[k]))
             x = yr.detach()

@@ -17,7 +17,8 @@
 #include "../radtts_b200/csrc/rowgemm_tc.cuh"
 
 namespace rb {
-long long g_launches = 0;   // the library defines this in capi.cu
+long long g_launches = 0;   // the library defines these in capi.cu
+int g_gemm_tile_select = 1;
 
 // bias + softplus + bf16 store: the arithmetic of the in_layer epilogue without the frame-plan lookups
 struct EpiMicro {
@@ -39,11 +40,12 @@ struct EpiMicro {
 static int launch_micro(const GemmDesc& d, const EpiMicro& epi, int bn, int grid, cudaStream_t st) {
   TcParams p{};
   p.nseg = d.nseg; p.N = d.N; p.rows_alloc = d.rows_alloc; p.plan = nullptr;
-  p.bn = bn; p.n_tiles_n = ceil_div(d.N, bn);
+  p.bn[0] = bn; p.ncand = 1;                     // one candidate: the width under test (the ring depth follows from it)
   RB_TRY(make_map_bf16(d.seg[0].a, d.seg[0].lda, d.seg[0].lda, d.rows_alloc, kTcBM, &p.amap[0]));
   for (int i = 1; i < kTcMaxMaps; ++i) p.amap[i] = p.amap[0];
   for (int s = 0; s < d.nseg; ++s) p.seg[s] = TcSeg{0, d.seg[s].shift, d.seg[s].kcol, d.seg[s].klen / kTcBK};
-  RB_TRY(make_map_bf16(d.w, d.ldw, d.ldw, d.N, bn, &p.wmap));
+  RB_TRY(make_map_bf16(d.w, d.ldw, d.ldw, d.N, bn, &p.wmap[0]));
+  for (int c = 1; c < kTcCand; ++c) { p.wmap[c] = p.wmap[0]; p.bn[c] = bn; }
   static bool configured = false;
   if (!configured) {
     RB_CUDA(cudaFuncSetAttribute(rowgemm_tc_kernel<EpiMicro>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));

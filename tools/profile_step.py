@@ -63,3 +63,48 @@ print("total kernel time %.2f ms, %d launches; rb:: %.2f ms (%d launches); other
     sum(e.count for e in ks if "rb::" not in e.key)))
 for e in ks[:130]:
     print("%9.1f us %5d x %8.2f  %s" % (e.device_time_total, e.count, e.device_time_total / e.count, e.key[:140]))
+
+# ---- attribution of the non-library kernels: which torch op / autograd node / region launched them (from the trace events)
+if os.environ.get("PROFILE_ATTRIB", "1") == "1":
+    import collections
+    import json
+    import tempfile
+    path = os.path.join(tempfile.gettempdir(), "step_trace.json")
+    prof.export_chrome_trace(path)
+    ev = json.load(open(path))["traceEvents"]
+    kern = [e for e in ev if e.get("cat") == "kernel"]
+    launches = {e["args"]["correlation"]: e for e in ev if e.get("cat") == "cuda_runtime" and "correlation" in e.get("args", {})}
+    cpu = [e for e in ev if e.get("cat") in ("cpu_op", "user_annotation") and "dur" in e]
+    by_tid = collections.defaultdict(list)
+    for e in cpu:
+        by_tid[e["tid"]].append(e)
+    for v in by_tid.values():
+        v.sort(key=lambda e: e["ts"])
+    agg = collections.defaultdict(lambda: [0.0, 0])
+    for k in kern:
+        if "rb::" in k["name"]:
+            continue
+        la = launches.get(k["args"].get("correlation"))
+        chain = []
+        if la is not None:
+            for e in by_tid.get(la["tid"], ()):
+                if e["ts"] > la["ts"]:
+                    break
+                if e["ts"] + e["dur"] >= la["ts"]:
+                    chain.append(e["name"])
+        outer = [c for c in chain if c.startswith("REGION:") or c.endswith("Backward") or "Backward" in c or c.startswith("autograd::engine")]
+        key = (" > ".join(outer[-2:]) if outer else "(top)", chain[-1] if chain else "?", k["name"][:60])
+        agg[key][0] += k["dur"]
+        agg[key][1] += 1
+    print("==== non-library kernels by launching op (us, launches)")
+    tot_o = sum(v[0] for v in agg.values())
+    print("total %.1f us" % tot_o)
+    for key, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:120]:
+        print("%9.1f us %4d x  %-60s | %-40s | %s" % (v[0], v[1], key[0][:60], key[1][:40], key[2]))
+    reg = collections.defaultdict(lambda: [0.0, 0])
+    for key, v in agg.items():
+        reg[key[0]][0] += v[0]
+        reg[key[0]][1] += v[1]
+    print("==== non-library kernels by region")
+    for key, v in sorted(reg.items(), key=lambda kv: -kv[1][0])[:40]:
+        print("%9.1f us %4d x  %s" % (v[0], v[1], key))
