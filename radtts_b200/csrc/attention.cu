@@ -47,9 +47,18 @@ __device__ __forceinline__ void stage_qk(const float* __restrict__ q, const floa
 // four FMAs (the one-frame version was bound by shared-memory loads: one LDS per FMA), and the squared distance is
 // expanded, |q - k|^2 = |q|^2 + |k|^2 - 2 q.k -- one FMA per (frame, key, channel) instead of a subtract and an FMA.
 // The prior row of each frame is fetched into registers BEFORE the channel loop, which hides its DRAM latency.
-constexpr int kFwdRows = 32;
+// Frames per warp: with four, a channel step is 11 shared-memory wavefronts for 44 FMA instructions per warp; eight (12
+// wavefronts for 88 FMAs, prior rows fetched in the epilogue because the accumulators fill the register budget) was
+// measured SLOWER at 64 x 2000 x 300 (0.62 vs 0.43 ms): one 8-warp CTA per SM cannot hide the epilogue's latencies.  What
+// the four-frame kernel spends outside the FMAs is the epilogue -- two exponentials and a logarithm per cell -- which
+// uses the MUFU forms (ex2 / lg2.approx, relative error 2^-21: far inside the 1e-3 parity bound of this kernel).
 constexpr int kFwdThreads = 256;
-constexpr int kFwdFr = 4;
+template <int NJ>
+struct FwdCfg {
+  static constexpr int kFr = 4;                                // frames per warp (8 measured slower: see below)
+  static constexpr int kRows = (kFwdThreads / 32) * kFr;       // frames per tile
+  static constexpr bool kPrefetchPrior = true;
+};
 
 template <int NJ>
 __global__ void __launch_bounds__(kFwdThreads) convattn_fwd_kernel(const float* __restrict__ q_enc, const float* __restrict__ k_enc,
@@ -57,6 +66,8 @@ __global__ void __launch_bounds__(kFwdThreads) convattn_fwd_kernel(const float* 
                                                                    int C, int T1, int T2, float temp, float* __restrict__ attn,
                                                                    float* __restrict__ logprob, float* __restrict__ lse_out) {
   extern __shared__ __align__(16) float sm[];
+  constexpr int kFwdFr = FwdCfg<NJ>::kFr, kFwdRows = FwdCfg<NJ>::kRows;
+  constexpr bool kPrefetch = FwdCfg<NJ>::kPrefetchPrior;
   const int T2p = NJ * 32;
   float* ks = sm;                                   // [C][T2p]
   float* qs = sm + (size_t)C * T2p;                 // [C][kFwdRows]
@@ -90,8 +101,8 @@ __global__ void __launch_bounds__(kFwdThreads) convattn_fwd_kernel(const float* 
     __syncthreads();
     if (t1_0 + r0 >= T1) continue;
     // prior rows of this warp's frames, in flight underneath the channel loop
-    float pr[kFwdFr][NJ];
-    if (prior) {
+    float pr[kPrefetch ? kFwdFr : 1][NJ];
+    if (prior && kPrefetch) {
 #pragma unroll
       for (int f = 0; f < kFwdFr; ++f) {
         const int t1 = t1_0 + r0 + f;
@@ -111,8 +122,12 @@ __global__ void __launch_bounds__(kFwdThreads) convattn_fwd_kernel(const float* 
       for (int j = 0; j < NJ; ++j) dot[f][j] = 0.f;
     }
     for (int c = 0; c < C; ++c) {
-      const float4 q4 = *reinterpret_cast<const float4*>(qs + (size_t)c * kFwdRows + r0);
-      const float qv[kFwdFr] = {q4.x, q4.y, q4.z, q4.w};
+      float qv[kFwdFr];
+#pragma unroll
+      for (int f = 0; f < kFwdFr; f += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(qs + (size_t)c * kFwdRows + r0 + f);
+        qv[f] = q4.x; qv[f + 1] = q4.y; qv[f + 2] = q4.z; qv[f + 3] = q4.w;
+      }
       const float* kr = ks + (size_t)c * T2p + lane;
 #pragma unroll
       for (int f = 0; f < kFwdFr; ++f) qn[f] = fmaf(qv[f], qv[f], qn[f]);
@@ -136,17 +151,24 @@ __global__ void __launch_bounds__(kFwdThreads) convattn_fwd_kernel(const float* 
         if (lane + 32 * j < T2) m = fmaxf(m, d[j]);
       }
       if (prior) {
+        if (!kPrefetch) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int t2 = lane + 32 * j;
+            pr[0][j] = t2 < T2 ? __ldg(prior + row_off + t2) : 0.f;
+          }
+        }
         m = warp_max(m);
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
-          if (lane + 32 * j < T2) s += expf(d[j] - m);
+          if (lane + 32 * j < T2) s += __expf(d[j] - m);
         s = warp_sum(s);
-        const float lse = m + logf(s);
+        const float lse = m + __logf(s);
         if (lane == 0 && lse_out) lse_out[(size_t)b * T1 + t1] = lse;
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
-          d[j] = (lane + 32 * j < T2) ? (d[j] - lse) + logf(pr[f][j] + 1e-8f) : -CUDART_INF_F;
+          d[j] = (lane + 32 * j < T2) ? (d[j] - lse) + __logf(pr[kPrefetch ? f : 0][j] + 1e-8f) : -CUDART_INF_F;
       } else {
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
@@ -163,7 +185,7 @@ __global__ void __launch_bounds__(kFwdThreads) convattn_fwd_kernel(const float* 
       float s2 = 0.f;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        d[j] = (lane + 32 * j < klen) ? expf(d[j] - m2) : 0.f;
+        d[j] = (lane + 32 * j < klen) ? __expf(d[j] - m2) : 0.f;
         s2 += d[j];
       }
       s2 = warp_sum(s2);
@@ -312,6 +334,7 @@ __global__ void __launch_bounds__(256) convattn_bwd_cols_kernel(const float* __r
 template <int NJ>
 static int launch_fwd(const float* q, const float* k, const float* prior, const int64_t* key_lens, int B, int C, int T1,
                       int T2, float temp, float* attn, float* logprob, float* lse, cudaStream_t st) {
+  constexpr int kFwdRows = FwdCfg<NJ>::kRows;
   const size_t smem = ((size_t)C * NJ * 32 + (size_t)C * kFwdRows + (size_t)NJ * 32) * sizeof(float);
   if (smem > (size_t)kSmemBudget) return RADTTS_ERR_UNSUPPORTED;
   static size_t configured = 0;
