@@ -484,10 +484,18 @@ static int wn_and_coupling(const radtts_flow_dims& d, const uint8_t* base, const
   g.seg[0] = Seg{r, nl * nc, 0, 0, nl * nc};
   g.w = base + L.w_end; g.ldw = nl * nc; g.N = d.z_ld;
   {
-    EpiCoupling e{reinterpret_cast<const float*>(base + L.b_end), inverse ? buf.zin : buf.zmid,
-                  inverse ? buf.zmid : buf.zout, inverse ? nullptr : buf.log_s, inverse ? nullptr : buf.params,
-                  d.c_off, h, d.z_ld, inverse, d.scaling, meta};
-    RB_TRY((run_gemm<T>(g, e, st)));
+    const float* b_end = reinterpret_cast<const float*>(base + L.b_end);
+    const float* zsrc = inverse ? buf.zin : buf.zmid;
+    float* zdst = inverse ? buf.zmid : buf.zout;
+    float* ls = inverse ? nullptr : buf.log_s;
+    float* pr = inverse ? nullptr : buf.params;
+    constexpr bool kFast = sizeof(T) == 2;
+    switch (d.scaling) {
+      case 0: RB_TRY((run_gemm<T>(g, EpiCouplingT<kFast, 0>{b_end, zsrc, zdst, ls, pr, d.c_off, h, d.z_ld, inverse, meta}, st))); break;
+      case 1: RB_TRY((run_gemm<T>(g, EpiCouplingT<kFast, 1>{b_end, zsrc, zdst, ls, pr, d.c_off, h, d.z_ld, inverse, meta}, st))); break;
+      case 2: RB_TRY((run_gemm<T>(g, EpiCouplingT<kFast, 2>{b_end, zsrc, zdst, ls, pr, d.c_off, h, d.z_ld, inverse, meta}, st))); break;
+      default: RB_TRY((run_gemm<T>(g, EpiCouplingT<kFast, 3>{b_end, zsrc, zdst, ls, pr, d.c_off, h, d.z_ld, inverse, meta}, st))); break;
+    }
   }
   return 0;
 }

@@ -222,23 +222,37 @@ struct EpiInvConv {
 // `end` conv + affine coupling.  Columns are interleaved pairs (2c: raw scale, 2c+1: translation) so that a
 // chunk always holds complete channels.  scaling 'tanh': s = tanh(x) + 1 + 1e-6 (reference common.py:782-784).
 //   forward : z1' = s * z1 + b, log_s = log s          inverse : z1 = (z1' - b) / s
-struct EpiCoupling {
+// kFast (the bf16 tensor-core engine): MUFU forms of tanh / exp / log (relative error ~1e-6 -- the engine's operands are
+// bf16), and the scaling mode dispatched ONCE per call.  With the libm forms and the four scaling modes expanded inside the
+// fully unrolled chunk loops this epilogue was 23 K SASS instructions: it missed the instruction cache all the way
+// through (ncu: `stalled_no_instruction` the top stall) and made the 160-wide `end` GEMM take 84 us where the same GEMM
+// with a plain epilogue takes 38 (tools/gemm_micro.cu, last problem).
+// The scaling mode S is a template parameter as well (the host picks the instantiation): one variant per kernel keeps the
+// unrolled epilogue at a quarter of the code.
+template <bool kFast, int S>
+struct EpiCouplingT {
   const float* bias;      // interleaved, length 2h (padded with zeros to N)
   const float* zsrc;      // [rows][160]: z1 is read from column c_off + h + c
   float* zdst;            // [rows][160]: written at the same column
   float* log_s;           // [rows][80] (forward only, may be null)
   float* params;          // [rows][160] raw (x, b) pairs saved for backward (may be null)
   int c_off, h, zld;
-  int inverse;
-  int scaling;            // 0 tanh, 1 exp, 2 sigmoid, 3 translate (reference common.py:775-787)
+  int inverse;            // S: 0 tanh, 1 exp, 2 sigmoid, 3 translate (reference common.py:775-787)
   RowMeta meta;
   __device__ __forceinline__ RowState prep(int row) const { return RowState{meta.valid(row), 1.f}; }
   __device__ __forceinline__ const float* colvec() const { return bias; }
-  __device__ __forceinline__ void scale_of(float x, float& s, float& lsv) const {
-    if (scaling == 0) { s = (tanhf(x) + 1.f) + 1e-6f; lsv = logf(s); }
-    else if (scaling == 1) { s = expf(x); lsv = x; }
-    else if (scaling == 2) { s = 1.f / (1.f + expf(-(x + 10.f))) + 1e-6f; lsv = logf(s); }
-    else { s = 1.f; lsv = 0.f; }
+  static __device__ __forceinline__ void scale_of(float x, float& s, float& lsv) {
+    if (kFast) {
+      if (S == 0) { s = ((1.f - __fdividef(2.f, __expf(2.f * x) + 1.f)) + 1.f) + 1e-6f; lsv = __logf(s); }
+      else if (S == 1) { s = __expf(x); lsv = x; }
+      else if (S == 2) { s = __fdividef(1.f, 1.f + __expf(-(x + 10.f))) + 1e-6f; lsv = __logf(s); }
+      else { s = 1.f; lsv = 0.f; }
+    } else {
+      if (S == 0) { s = (tanhf(x) + 1.f) + 1e-6f; lsv = logf(s); }
+      else if (S == 1) { s = expf(x); lsv = x; }
+      else if (S == 2) { s = 1.f / (1.f + expf(-(x + 10.f))) + 1e-6f; lsv = logf(s); }
+      else { s = 1.f; lsv = 0.f; }
+    }
   }
   template <int W>
   __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[W], const RowState& rs,
@@ -273,7 +287,7 @@ struct EpiCoupling {
         if (ok) {
           float sc, lsv;
           scale_of(x, sc, lsv);
-          if (inverse) outv[i] = (z1[i] - b) / sc;
+          if (inverse) outv[i] = kFast ? __fdividef(z1[i] - b, sc) : (z1[i] - b) / sc;
           else { outv[i] = sc * z1[i] + b; ls[i] = lsv; }
         }
         pv[2 * i] = ok ? x : 0.f;

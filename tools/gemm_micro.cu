@@ -19,6 +19,7 @@
 namespace rb {
 long long g_launches = 0;   // the library defines these in capi.cu
 int g_gemm_tile_select = 1;
+int g_gemm_prefetch_a = 1;
 
 // bias + softplus + bf16 store: the arithmetic of the in_layer epilogue without the frame-plan lookups
 struct EpiMicro {
@@ -78,7 +79,11 @@ int main(int argc, char** argv) {
   // column tiles: 37, 74, 111 row tiles)
   for (int tiles_m : {85, 37, 74, 111}) probs.push_back({tiles_m * 128, 1024, 1024, 5, 2});
   probs.push_back({85 * 128, 1024, 1024, 1, 1});   // res_skip: K = 1024
-  const int bns[] = {256, 240, 224, 208, 192, 176, 160, 144, 128, 96, 64};
+  probs.push_back({85 * 128, 4096, 160, 1, 1});    // `end`: K = 4 x 1024 concatenated skip buffer, N = 160, one tile per CTA
+  const int bns_all[] = {256, 240, 224, 208, 192, 176, 160, 144, 128, 96, 64};
+  const int bns_quick[] = {256, 208, 160};
+  const bool quick = argc > 2;
+  std::vector<int> bns(quick ? std::begin(bns_quick) : std::begin(bns_all), quick ? std::end(bns_quick) : std::end(bns_all));
 
   for (const Problem& pr : probs) {
     const int K = pr.taps * pr.C;
@@ -103,6 +108,7 @@ int main(int argc, char** argv) {
 
     for (int bn : bns) {
       if (pr.taps == 1 && bn < 128) continue;
+      if (bn > pr.N) continue;
       const int tiles = (pr.rows / 128) * ceil_div(pr.N, bn);
       const int grid = tiles < kNumSMs ? tiles : kNumSMs;
       cudaMemsetAsync(dO, 0, (size_t)pr.rows * pr.N * 2, st);
