@@ -444,7 +444,7 @@ def train_leg(name, args, world, rank, local, device, steps, with_attributes=Fal
         if name != "radtts" else None
     ts = TrainStep(model, configs.LOSS_WEIGHTS, bf16=True, ddp=world > 1, device_ids=[local] if world > 1 else None,
                    capturable=use_graph, loss_kwargs=lk, probe_batch=dev_batches[0] if name != "radtts" else None,
-                   deferred_update=not args.no_deferred_update)
+                   deferred_update=args.deferred_update)
     graph_note = "eager"
     if use_graph:
         try:
@@ -505,9 +505,10 @@ def main():
     ap.add_argument("--t2", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
-    ap.add_argument("--no-deferred-update", action="store_true",
-                    help="apply the whole RAdam update at the end of each step (default: the flow-parameter region is applied "
-                         "at the top of the next step, underneath its text encoder / attention / context LSTM)")
+    ap.add_argument("--deferred-update", action="store_true",
+                    help="TrainStep(deferred_update=True): the flow-parameter region of each RAdam update is applied at the top "
+                         "of the next step, underneath its text encoder / attention / context LSTM, and flushed inside the "
+                         "timed region (default: the whole update at the end of each step; measured equal within noise)")
     ap.add_argument("--no-extras", action="store_true", help="headline train step only (no cfg3 / cfg4 / infer / sweep legs)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -590,7 +591,7 @@ def main():
                 "loss_last": head["loss_last"], "extra": extra or None}
         line["config"]["global_batch"] = args.batch * world
         line["config"]["execution"] = head["execution"]
-        line["config"]["optimizer_update"] = ("whole update at the end of the step" if args.no_deferred_update else
+        line["config"]["optimizer_update"] = ("whole update at the end of the step" if not args.deferred_update else
                                               "flow-parameter region applied at the top of the next step (same kernels, "
                                               "pipelined); the last one is flushed inside the timed region")
         print(json.dumps(line))

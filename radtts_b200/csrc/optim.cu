@@ -96,8 +96,19 @@ extern "C" int radtts_radam_step_ex(float* p, float* g, float* m, float* v, size
   // A pending (pipelined) update runs UNDERNEATH other kernels: 2 CTAs per SM (35 K registers, 512 threads) leave room for
   // them on every SM; an update nothing can overlap takes 6 CTAs per SM for the bytes in flight HBM wants.
   static const int kPipelinedCtas = [] { const char* e = std::getenv("RADTTS_RADAM_PIPELINED_CTAS"); return e ? atoi(e) : 2; }();
+  // An SM changes its L1 / shared-memory split only when it is empty.  This kernel uses no shared memory, so by default its
+  // CTAs would configure every SM for the largest L1 -- and every kernel of the step's front end that needs a few KB of
+  // shared memory would wait for the whole update to drain (measured: the first front-end kernel started 1 ms late).  Ask
+  // for the largest shared-memory carve-out instead; a streaming kernel has no use for L1.
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    RB_CUDA(cudaFuncSetAttribute(radam_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carveout_set = true;
+  }
+  static const int kPipelinedGrid = [] { const char* e = std::getenv("RADTTS_RADAM_PIPELINED_GRID"); return e ? atoi(e) : 0; }();
   const int ctas_per_sm = enable ? kPipelinedCtas : 6;
-  radam_kernel<<<kNumSMs * ctas_per_sm, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale,
+  const int grid = (enable && kPipelinedGrid > 0) ? kPipelinedGrid : kNumSMs * ctas_per_sm;
+  radam_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale,
                                                       enable, zero_grad);
   RB_TRY(after_launch());
   if (bump) {
