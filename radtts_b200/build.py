@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "-I", INCLUDE, "-I", CSRC,
-]
+] + os.environ.get("RADTTS_NVCC_EXTRA", "").split()      # e.g. RADTTS_NVCC_EXTRA=-DRB_LSTM_TIMELINE=1 (diagnostic builds)
 
 
 def _nvcc():

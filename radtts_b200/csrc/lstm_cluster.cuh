@@ -297,6 +297,16 @@ lstm_fwd_cluster_reg_kernel(const float* __restrict__ gx, const float* __restric
   uint32_t* hs = reinterpret_cast<uint32_t*>(smraw);
   uint32_t* st = hs + (size_t)2 * kSplit * hs_part;
   float* red = reinterpret_cast<float*>(st + (size_t)2 * kSplit * st_part);      // [UG][2 dest halves][32][8]
+  // Global traffic of a step goes through shared memory (measured before: 8 scalar loads + 12 scalar stores per thread
+  // and step, 4-byte pieces of 6 arrays with 8 KB strides -- issuing them took 3.4 us of the 5.1 us step at H = 520):
+  //   gxs [2][16 batch rows][4 gates][U] (+4 floats per row: bank spread)  next step's input-projection slice, fetched
+  //        one step ahead with 16-byte cp.async, U * 4-byte runs;
+  //   outs [16][6][U] (+4)   i, f, g, o, c, h of this step, written out by all threads as 16-byte stores of whole runs.
+  const int U = 8 * UG;
+  const int gx_ld = 4 * U + 4, out_ld = 6 * U + 4;
+  float* gxs = red + (size_t)UG * 2 * 32 * 8;
+  float* outs = gxs + (size_t)2 * 16 * gx_ld;
+  const int U_own = 8 * n_own, u0 = g_first * 8;
   __shared__ __align__(8) uint64_t bar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ug = warp >> 1, half = warp & 1;
@@ -339,17 +349,64 @@ lstm_fwd_cluster_reg_kernel(const float* __restrict__ gx, const float* __restric
   __syncthreads();
   cl_sync();
 
+  // gx slice of time step tt -> gxs[buf]: (row r, gate, 4 units) per 16-byte copy; rows beyond B are never read.
+  // The (row, gate / array, vector) decomposition of a thread's copies is the same every step: worked out once, here
+  // (run-time divisions inside the time loop cost more than the copies).
+  const int v_per_run = U_own / 4, n_vec = 16 * 4 * v_per_run;
+  constexpr int kMaxIn = 3, kMaxOut = 4;          // 16 * 4 * 10 / 320 = 2 resp. 16 * 6 * 10 / 320 = 3 at H = 520
+  int in_src[kMaxIn], in_dst[kMaxIn];             // element offsets: global (without the time-step term), gxs (buffer 0)
+#pragma unroll
+  for (int j = 0; j < kMaxIn; ++j) {
+    const int i = tid + j * (int)blockDim.x;
+    in_src[j] = -1; in_dst[j] = 0;
+    if (i < n_vec) {
+      const int v = i % v_per_run, gate = (i / v_per_run) & 3, r = i / (4 * v_per_run);
+      if (b0 + r < B) {
+        in_src[j] = ((b0 + r) * 4 + gate) * H + u0 + 4 * v;
+        in_dst[j] = r * gx_ld + gate * U + 4 * v;
+      }
+    }
+  }
+  const int n_arr = gates_save ? 6 : 1;
+  int out_src[kMaxOut], out_dst[kMaxOut], out_k[kMaxOut];
+#pragma unroll
+  for (int j = 0; j < kMaxOut; ++j) {
+    const int i = tid + j * (int)blockDim.x;
+    out_src[j] = -1; out_dst[j] = 0; out_k[j] = 0;
+    if (i < 16 * n_arr * v_per_run) {
+      const int v = i % v_per_run, k0 = (i / v_per_run) % n_arr, r = i / (n_arr * v_per_run);
+      const int k = gates_save ? k0 : 5, bb = b0 + r;
+      if (bb < B) {
+        out_src[j] = r * out_ld + k * U + 4 * v;
+        out_k[j] = k;
+        out_dst[j] = k < 4 ? (bb * 4 + k) * H + u0 + 4 * v : (k == 4 ? bb * H + u0 + 4 * v : (bb * 2 + dir) * H + u0 + 4 * v);
+      }
+    }
+  }
+  // (64 UG threads: 128 UG input and 192 UG output vectors per step always fit in kMaxIn / kMaxOut rounds)
+  auto prefetch_gx = [&](int tt, int buf) {
+    const float* base = gx + ((size_t)dir * T + tt) * B * 4 * H;
+    const uint32_t sbase = smem_u32(gxs + (size_t)buf * 16 * gx_ld);
+#pragma unroll
+    for (int j = 0; j < kMaxIn; ++j)
+      if (in_src[j] >= 0)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sbase + 4u * (uint32_t)in_dst[j]), "l"(base + in_src[j]) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch_gx(dir == 0 ? 0 : T - 1, 0);
+#if RB_LSTM_TIMELINE
+  long long dacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c_prev = 0;
+#endif
   for (int s = 0; s < T; ++s) {
     const int t = dir == 0 ? s : T - 1 - s;
     const int cur = s & 1, nxt = cur ^ 1;
-    float gxv[4][2];
-#pragma unroll
-    for (int gate = 0; gate < 4; ++gate)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int b = b0 + half * 8 + 2 * q + e;
-        gxv[gate][e] = (active && b < B) ? __ldg(gx + (((size_t)dir * T + t) * B + b) * 4 * H + gate * H + u) : 0.f;
-      }
+    long long c_top = 0;
+    if (RB_LSTM_TIMELINE) c_top = clock64();
+    // next step's slice goes into the other buffer (its readers finished before the barriers of step s - 1); this step's
+    // slice (committed one step ago) must have landed before the partial-sum barrier below publishes it to every thread
+    if (s + 1 < T) prefetch_gx(dir == 0 ? s + 1 : T - 2 - s, nxt);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     const bool dbg = RB_LSTM_TIMELINE && (tid == 0 && rank == 0 && blockIdx.y == 0 && blockIdx.z == 0);
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
     if (dbg) c0 = clock64();
@@ -397,12 +454,22 @@ lstm_fwd_cluster_reg_kernel(const float* __restrict__ gx, const float* __restric
       for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          rdst[mt * 4 + r] = acc[mt][1 - half][0][r] + acc[mt][1 - half][1][r];
-          mine[mt][r] = acc[mt][half][0][r] + acc[mt][half][1][r];
+          // selects, not acc[mt][half]: a run-time index would put the accumulators in local memory
+          const float s0 = acc[mt][0][0][r] + acc[mt][0][1][r], s1 = acc[mt][1][0][r] + acc[mt][1][1][r];
+          rdst[mt * 4 + r] = half ? s0 : s1;
+          mine[mt][r] = half ? s1 : s0;
         }
       }
     }
     __syncthreads();
+    float gxv[4][2];
+#pragma unroll
+    for (int gate = 0; gate < 4; ++gate)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = half * 8 + 2 * q + e;
+        gxv[gate][e] = (active && b0 + r < B) ? gxs[((size_t)cur * 16 + r) * gx_ld + gate * U + ug * 8 + g] : 0.f;
+      }
     {
       const float* rsrc = red + (((size_t)ug * 2 + half) * 32 + lane) * 8;
 #pragma unroll
@@ -423,6 +490,10 @@ lstm_fwd_cluster_reg_kernel(const float* __restrict__ gx, const float* __restric
       cn[e] = on ? fg[e] * c_state[e] + ig[e] * gg[e] : 0.f;
       hval[e] = on ? og[e] * cl_tanh_fast(cn[e]) : 0.f;
       c_state[e] = cn[e];
+      if (active) {
+        float* o = outs + (size_t)(half * 8 + 2 * q + e) * out_ld + ug * 8 + g;
+        o[0] = ig[e]; o[U] = fg[e]; o[2 * U] = gg[e]; o[3 * U] = og[e]; o[4 * U] = cn[e]; o[5 * U] = hval[e];
+      }
       const float partner = __shfl_down_sync(0xffffffffu, hval[e], 4);
       if (active && (g & 1) == 0) {
         uint32_t hi, lo;
@@ -447,26 +518,33 @@ lstm_fwd_cluster_reg_kernel(const float* __restrict__ gx, const float* __restric
         }
       }
     }
-    if (active) {
+    {
+      // outs was completed before the barrier above: whole U-float runs as 16-byte stores, all threads
+      float* gbase = gates_save ? gates_save + ((size_t)dir * T + t) * B * 4 * H : nullptr;
+      float* cbase = c_save ? c_save + ((size_t)dir * T + t) * B * H : nullptr;
+      float* hbase = h_all + (size_t)t * B * 2 * H;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int b = b0 + half * 8 + 2 * q + e;
-        if (b < B) {
-          if (gates_save) {
-            float* gs = gates_save + (((size_t)dir * T + t) * B + b) * 4 * H;
-            gs[u] = ig[e]; gs[H + u] = fg[e]; gs[2 * H + u] = gg[e]; gs[3 * H + u] = og[e];
-            c_save[(((size_t)dir * T + t) * B + b) * H + u] = cn[e];
-          }
-          h_all[((size_t)t * B + b) * 2 * H + dir * H + u] = hval[e];
+      for (int j = 0; j < kMaxOut; ++j)
+        if (out_src[j] >= 0) {
+          const float4 val = *reinterpret_cast<const float4*>(outs + out_src[j]);
+          float* dst = (out_k[j] < 4 ? gbase : (out_k[j] == 4 ? cbase : hbase)) + out_dst[j];
+          *reinterpret_cast<float4*>(dst) = val;
         }
-      }
     }
+#if RB_LSTM_TIMELINE
     if (dbg) {
       c4 = clock64();
-      if (s == 0) for (int i = 0; i < 6; ++i) g_cl_dbg[i] = 0;
-      g_cl_dbg[0] += c1 - c0; g_cl_dbg[1] += c2 - c1; g_cl_dbg[2] += c3 - c2; g_cl_dbg[4] += c4 - c3; g_cl_dbg[5] += 1;
+      dacc[0] += c1 - c0; dacc[1] += c2 - c1; dacc[2] += c3 - c2; dacc[4] += c4 - c3; dacc[5] += 1;
+      dacc[3] += c0 - c_top;                      // prefetch issue
+      if (s > 0) dacc[6] += c_top - c_prev;       // loop back edge
+      c_prev = c4;
     }
+#endif
   }
+#if RB_LSTM_TIMELINE
+  if (tid == 0 && rank == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    for (int i = 0; i < 8; ++i) g_cl_dbg[i] = (unsigned long long)dacc[i];
+#endif
   cl_sync();
 }
 
@@ -756,7 +834,9 @@ inline int lstm_cluster_forward(const float* gx, const float* whh, const int* le
   {
     // register-resident weights when an instantiation covers this H: KSH k-steps per warp half, 2 KSH >= ceil(H / 16)
     auto reg_smem = [&](int ksh) {
-      return (size_t)split * ((size_t)2 * (4 * ksh) * 2 * 32 * 4 + (size_t)2 * d.UG * 2 * 32 * 4) + (size_t)d.UG * 2 * 32 * 8 * 4;
+      const size_t U = (size_t)8 * d.UG;
+      return (size_t)split * ((size_t)2 * (4 * ksh) * 2 * 32 * 4 + (size_t)2 * d.UG * 2 * 32 * 4) + (size_t)d.UG * 2 * 32 * 8 * 4 +
+             ((size_t)2 * 16 * (4 * U + 4) + (size_t)16 * (6 * U + 4)) * 4;
     };
     if (split == 1 && d.KS <= 34 && d.KS > 16)
       return cl_launch(lstm_fwd_cluster_reg_kernel<1, 17>, d, 64 * d.UG, reg_smem(17), st, gx, whh, lens, d, h_all, gates_save, c_save);

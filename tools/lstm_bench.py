@@ -50,7 +50,8 @@ def run(T, B, H, prec, iters=10):
     dbg = (ctypes.c_ulonglong * 16)()
     L.radtts_lstm_debug_timeline(dbg)
     if dbg[5]:
-        print("   fwd cycles/step: wait %.0f  mma %.0f  gates %.0f  send+stores %.0f" % tuple(dbg[i] / dbg[5] for i in (0, 1, 2, 4)))
+        print("   fwd cycles/step: wait %.0f  mma %.0f  gates %.0f  send+stores %.0f  gx-load issue %.0f  back edge %.0f" %
+              tuple(dbg[i] / dbg[5] for i in (0, 1, 2, 4, 3, 6)))
     return out, float(h_all.double().abs().sum()), float(dg.double().abs().sum())
 
 
