@@ -51,9 +51,11 @@ class _BiLSTMFn(torch.autograd.Function):
         dev = x_tm.device
         need_bwd = any(ctx.needs_input_grad)
         # input projection for every step: one GEMM per direction (plain library GEMM; autocast-aware)
+        # (bias added in the GEMM's epilogue: a separate add is a 0.4 GB pass over gx at the context LSTM's size)
         with _rnn_matmul_precision():
-            gx = (torch.matmul(x_tm.reshape(1, T * B, -1), w_ih.transpose(1, 2)).float()
-                  + bias.float()[:, None, :]).reshape(2, T, B, 4 * H).contiguous()
+            xin = x_tm.reshape(1, T * B, -1).expand(2, -1, -1)
+            gx = torch.baddbmm(bias[:, None, :].to(x_tm.dtype), xin, w_ih.transpose(1, 2).to(x_tm.dtype))
+            gx = gx.float().reshape(2, T, B, 4 * H).contiguous()
         whh = w_hh.detach().float().contiguous()
         h_all = torch.empty((T, B, 2 * H), dtype=torch.float32, device=dev)
         gates = torch.empty((2, T, B, 4 * H), dtype=torch.float32, device=dev) if need_bwd else None
@@ -95,14 +97,16 @@ class _BiLSTMFn(torch.autograd.Function):
         dg2 = dg.reshape(2, T * B, 4 * H)
         dgm = dg2.to(mm)
         xf = x_tm.reshape(T * B, -1).to(mm)
-        # h_{t-1} in each direction's own time order
-        zeros = torch.zeros((1, B, H), dtype=torch.float32, device=dev)
-        h_prev_f = torch.cat((zeros, h_all[:-1, :, :H]), 0).reshape(T * B, H).to(mm)
-        h_prev_r = torch.cat((h_all[1:, :, H:], zeros), 0).reshape(T * B, H).to(mm)
+        # h_{t-1} in each direction's own time order: the first (forward) / last (reverse) step multiplies a zero state,
+        # so those B rows are simply left out of the product -- no zero-padded copies of h
+        h16 = h_all.to(mm)
+        h_prev_f = h16[:-1, :, :H].reshape((T - 1) * B, H)
+        h_prev_r = h16[1:, :, H:].reshape((T - 1) * B, H)
         with _rnn_matmul_precision():
-            d_x = torch.matmul(dgm, w_ih.to(mm)).float().sum(0).reshape(x_tm.shape).to(x_tm.dtype)
+            wm = w_ih.to(mm)
+            d_x = torch.addmm(dgm[0] @ wm[0], dgm[1], wm[1]).reshape(x_tm.shape).to(x_tm.dtype)   # sum over directions
             d_w_ih = torch.matmul(dgm.transpose(1, 2), xf).float()
-            d_w_hh = torch.stack((dgm[0].t() @ h_prev_f, dgm[1].t() @ h_prev_r)).float()
+            d_w_hh = torch.stack((dgm[0][B:].t() @ h_prev_f, dgm[1][:(T - 1) * B].t() @ h_prev_r)).float()
         d_bias = dg2.sum(1)
         return d_x, None, d_w_ih.to(w_ih.dtype), d_w_hh, d_bias
 
