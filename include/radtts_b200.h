@@ -14,7 +14,8 @@
  *     runtime call, <0 = RADTTS_ERR_* below;  no exceptions, no exit();
  *   - process-global state the library keeps: cached cudaFuncSetAttribute / driver entry points, a launch counter, ONE
  *     internal side stream + two events per device (res_skip back-fill fork/join of the flow step, captured like any
- *     other fork when the caller's stream is capturing), and a cache of TMA tensor maps keyed by (pointer, shape).
+ *     other fork when the caller's stream is capturing), a cache of TMA tensor maps keyed by (pointer, shape), and the
+ *     row-GEMM tuning switch (radtts_set_gemm_tile_select).
  *     Calls on different streams are safe; two threads calling flow-step entry points concurrently are not.
  */
 #ifndef RADTTS_B200_H_
