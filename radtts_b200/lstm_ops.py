@@ -4,6 +4,7 @@ Drop-in for `pad_packed_sequence(lstm(pack_padded_sequence(x, lens)))` on an nn.
 bidirectional=True, batch_first=True) module (reference radtts.py:284-293, common.py:359-371): same parameters
 (including the spectral-norm re-parameterisation hooks), same zero outputs beyond each length, same gradients."""
 import ctypes
+import os
 
 import torch
 
@@ -32,11 +33,107 @@ def supported(lstm, x):
             and lstm.hidden_size <= MAX_H and lstm.proj_size == 0)
 
 
+_weight_streams = {}
+
+
+def _spectral_hooks(lstm):
+    """{weight name: hook} when every forward pre-hook of the module is an old-style torch.nn.utils.spectral_norm hook over
+    dim 0 (what the reference puts on weight_hh_l0 / weight_hh_l0_reverse), else None."""
+    from torch.nn.utils.spectral_norm import SpectralNorm
+    hooks = {}
+    for h in lstm._forward_pre_hooks.values():
+        if not isinstance(h, SpectralNorm) or h.dim != 0:
+            return None
+        hooks[h.name] = h
+    return hooks or None
+
+
+class _SpectralWeight(torch.autograd.Function):
+    """weight = W / sigma, sigma = u^T W v with u, v constants (torch.nn.utils.spectral_norm.compute_weight) -- the value
+    comes precomputed from prefetch_weights (side stream, no autograd); this node only carries the gradient:
+    dL/dW = G / sigma - <G, W> / sigma^2 * u v^T.  One node on the consuming stream instead of ~25 small autograd nodes."""
+
+    @staticmethod
+    def forward(ctx, w_orig, u, v, sigma, w_eff):
+        ctx.save_for_backward(w_orig, u, v, sigma)
+        return w_eff.view_as(w_eff)
+
+    @staticmethod
+    def backward(ctx, g):
+        w, u, v, sigma = ctx.saved_tensors
+        g = g.to(w.dtype)
+        coef = (g * w).sum() / (sigma * sigma)
+        return g / sigma - coef * torch.outer(u, v), None, None, None, None
+
+
+def prefetch_weights(lstms, fp32=()):
+    """Starts the spectral-norm work of `lstms` NOW, on a side stream, for the bilstm() calls of the forward pass that is
+    starting: the power iteration (training), sigma and W / sigma -- ~30 tiny launches per LSTM that sat on the critical
+    path right in front of each recurrence (0.15 ms each in the step's timeline) although they depend on nothing but the
+    parameters.  Everything on the side stream runs WITHOUT autograd (nodes recorded on a second stream raced with the
+    main stream's backward in testing); the gradient comes from _SpectralWeight at the point of use.  `fp32`: modules
+    whose owner runs them with autocast disabled (the text encoder).  The power iteration still runs exactly once per
+    forward, as in the reference.  RADTTS.forward calls this first (training on CUDA)."""
+    if os.environ.get("RADTTS_NO_LSTM_PREFETCH"):
+        return
+    todo = []
+    for m in lstms:
+        if isinstance(m, torch.nn.LSTM) and m.weight_ih_l0.is_cuda and m._forward_pre_hooks:
+            hooks = _spectral_hooks(m)
+            if hooks is not None:
+                todo.append((m, hooks))
+    if not todo:
+        return
+    dev = todo[0][0].weight_ih_l0.device
+    side = _weight_streams.get(dev.index)
+    if side is None:
+        side = _weight_streams[dev.index] = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    F = torch.nn.functional
+    with torch.cuda.stream(side), torch.no_grad():
+        for m, hooks in todo:
+            with torch.autocast("cuda", enabled=torch.is_autocast_enabled() and not any(m is x for x in fp32)):
+                state = {}
+                for name, h in hooks.items():
+                    W = getattr(m, name + "_orig")
+                    u, v = getattr(m, name + "_u"), getattr(m, name + "_v")
+                    if m.training:
+                        for _ in range(h.n_power_iterations):
+                            v = F.normalize(torch.mv(W.t(), u), dim=0, eps=h.eps, out=v)
+                            u = F.normalize(torch.mv(W, v), dim=0, eps=h.eps, out=u)
+                        if h.n_power_iterations > 0:
+                            u, v = u.clone(), v.clone()
+                    sigma = torch.dot(u, torch.mv(W, v))
+                    state[name] = (u, v, sigma, W / sigma)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            m._rb_prefetched = (state, ev)
+
+
+def drop_prefetched(lstms):
+    """Forgets prefetched weights no bilstm() call consumed (a forward that skipped the module); the current stream still
+    waits for the side stream's in-place updates of the u / v buffers."""
+    for m in lstms:
+        pre = getattr(m, "_rb_prefetched", None) if m is not None else None
+        if pre is not None:
+            torch.cuda.current_stream(m.weight_ih_l0.device).wait_event(pre[1])
+            m._rb_prefetched = None
+
+
 def _effective_weights(lstm):
-    """Runs the module's forward pre-hooks (old-style spectral / weight norm recompute weight_hh_l0*) and returns
-    stacked (w_ih (2,4H,In), w_hh (2,4H,H), bias (2,4H)) with autograd links to the underlying parameters."""
-    for hook in lstm._forward_pre_hooks.values():
-        hook(lstm, ())
+    """Stacked (w_ih (2,4H,In), w_hh (2,4H,H), bias (2,4H)) with autograd links to the underlying parameters.  The module's
+    forward pre-hooks (old-style spectral / weight norm recompute weight_hh_l0*) either run here, or -- spectral norm
+    prefetched by prefetch_weights -- are replaced by one _SpectralWeight node per weight."""
+    pre = getattr(lstm, "_rb_prefetched", None)
+    if pre is not None:
+        lstm._rb_prefetched = None
+        state, ev = pre
+        torch.cuda.current_stream(lstm.weight_ih_l0.device).wait_event(ev)
+        for name, (u, v, sigma, w_eff) in state.items():
+            setattr(lstm, name, _SpectralWeight.apply(getattr(lstm, name + "_orig"), u, v, sigma, w_eff))
+    else:
+        for hook in lstm._forward_pre_hooks.values():
+            hook(lstm, ())
     w_ih = torch.stack((lstm.weight_ih_l0, lstm.weight_ih_l0_reverse))
     w_hh = torch.stack((lstm.weight_hh_l0, lstm.weight_hh_l0_reverse))
     bias = torch.stack((lstm.bias_ih_l0 + lstm.bias_hh_l0, lstm.bias_ih_l0_reverse + lstm.bias_hh_l0_reverse))
@@ -115,13 +212,22 @@ def bilstm(lstm, x, lens):
     """x (B, T, In) batch-first, lens (B,) -> (B, T, 2H) with zeros beyond each length."""
     w_ih, w_hh, bias = _effective_weights(lstm)
     lens32 = lens.to(device=x.device, dtype=torch.int32).contiguous()
+
+    def time_major(xb):
+        # ONE pass: batch-first -> time-major and, under autocast, fp32 -> bf16 (the input projection would cast it
+        # anyway; done here the transposed copy moves half the bytes and the GEMM's own cast disappears)
+        dt = torch.bfloat16 if (xb.is_cuda and torch.is_autocast_enabled() and xb.dtype == torch.float32) else xb.dtype
+        if os.environ.get("RADTTS_NO_LSTM_FUSED_CAST"):
+            return xb.transpose(0, 1).contiguous()
+        return torch.empty((xb.shape[1], xb.shape[0], xb.shape[2]), dtype=dt, device=xb.device).copy_(xb.transpose(0, 1))
+
     if x.shape[0] <= MAX_B:
-        x_tm = x.transpose(0, 1).contiguous()
+        x_tm = time_major(x)
         return _BiLSTMFn.apply(x_tm, lens32, w_ih, w_hh, bias).transpose(0, 1)
     # the kernel keeps <= 32 utterances per launch (one MMA N-tile): larger batches run in chunks, utterances being
     # independent (weight gradients accumulate across the chunks through autograd)
     outs = []
     for lo in range(0, x.shape[0], MAX_B):
-        x_tm = x[lo:lo + MAX_B].transpose(0, 1).contiguous()
+        x_tm = time_major(x[lo:lo + MAX_B])
         outs.append(_BiLSTMFn.apply(x_tm, lens32[lo:lo + MAX_B].contiguous(), w_ih, w_hh, bias).transpose(0, 1))
     return torch.cat(outs, 0)

@@ -7,7 +7,7 @@ state dict uses the reference names, so reference checkpoints load with load_sta
 import torch
 from torch import nn
 
-from . import alignment, ops
+from . import lstm_ops, alignment, ops
 from .attribute_prediction_model import get_attribute_prediction_model
 from .common import (AffineTransformationLayer, ConvAttention, Encoder, ExponentialClass, Invertible1x1Conv,
                      Invertible1x1ConvLUS, LengthRegulator, LinearNorm, _apply_lstm_norm, get_mask_from_lengths,
@@ -218,6 +218,10 @@ class RADTTS(nn.Module):
             # weight norm / LU composition / re-layout of all 8 flows start now, on a side stream, and finish underneath
             # the text encoder, the attention and the context LSTM
             prep = ops.begin_decoder_prep(self)
+        if mel.is_cuda and torch.is_grad_enabled():
+            # spectral-norm power iterations of the two BiLSTMs: off the critical path, on a side stream, now
+            enc_lstm = getattr(self.encoder, "lstm", None)
+            lstm_ops.prefetch_weights([enc_lstm, getattr(self, "context_lstm", None)], fp32=(enc_lstm,))
         speaker_vecs = self.encode_speaker(speaker_ids)
         text_enc, text_embeddings = self.encode_text(text, in_lens)
         log_s_list, log_det_W_list, z_mel = [], [], []
@@ -309,6 +313,7 @@ class RADTTS(nn.Module):
             energy_model_outputs = self.energy_pred_module(text_enc_time_expanded, speaker_vecs.detach(),
                                                            energy_avg, out_lens)
 
+        lstm_ops.drop_prefetched([getattr(self.encoder, "lstm", None), getattr(self, "context_lstm", None)])
         return {"z_mel": z_mel, "log_det_W_list": log_det_W_list, "log_s_list": log_s_list,
                 "duration_model_outputs": duration_model_outputs, "f0_model_outputs": f0_model_outputs,
                 "energy_model_outputs": energy_model_outputs, "vpred_model_outputs": vpred_model_outputs,
