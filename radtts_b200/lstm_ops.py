@@ -140,6 +140,25 @@ def _effective_weights(lstm):
     return w_ih, w_hh, bias
 
 
+_out_dtype_ok = [True]
+
+
+def _input_projection(x_tm, w_ih, bias):
+    """x (T, B, In) @ w_ih^T + bias for both directions -> (2, T * B, 4H) float32.  With bf16 operands the GEMM writes fp32
+    itself (aten::baddbmm.dtype: fp32 bias in the epilogue, no separate up-cast pass over the 0.2 GB result); a torch build
+    without that overload falls back to bf16 output + cast, once and for all."""
+    T, B, _ = x_tm.shape
+    xin = x_tm.reshape(1, T * B, -1).expand(2, -1, -1)
+    wt = w_ih.transpose(1, 2).to(x_tm.dtype)
+    if x_tm.dtype in (torch.bfloat16, torch.float16) and _out_dtype_ok[0]:
+        try:
+            with torch.autocast("cuda", enabled=False):
+                return torch.baddbmm(bias.float()[:, None, :].expand(-1, T * B, -1), xin, wt, out_dtype=torch.float32)
+        except (RuntimeError, TypeError):
+            _out_dtype_ok[0] = False
+    return torch.baddbmm(bias[:, None, :].to(x_tm.dtype), xin, wt).float()
+
+
 class _BiLSTMFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_tm, lens, w_ih, w_hh, bias):
@@ -150,9 +169,7 @@ class _BiLSTMFn(torch.autograd.Function):
         # input projection for every step: one GEMM per direction (plain library GEMM; autocast-aware)
         # (bias added in the GEMM's epilogue: a separate add is a 0.4 GB pass over gx at the context LSTM's size)
         with _rnn_matmul_precision():
-            xin = x_tm.reshape(1, T * B, -1).expand(2, -1, -1)
-            gx = torch.baddbmm(bias[:, None, :].to(x_tm.dtype), xin, w_ih.transpose(1, 2).to(x_tm.dtype))
-            gx = gx.float().reshape(2, T, B, 4 * H).contiguous()
+            gx = _input_projection(x_tm, w_ih, bias).reshape(2, T, B, 4 * H).contiguous()
         whh = w_hh.detach().float().contiguous()
         h_all = torch.empty((T, B, 2 * H), dtype=torch.float32, device=dev)
         gates = torch.empty((2, T, B, 4 * H), dtype=torch.float32, device=dev) if need_bwd else None
