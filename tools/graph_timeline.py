@@ -16,7 +16,7 @@ from radtts_b200.trainer import TrainStep
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/graph_timeline.json"
 dev = torch.device("cuda", 0)
 model = bench.make_model(dev).train()
-ts = TrainStep(model, configs.LOSS_WEIGHTS, bf16=True, capturable=True, deferred_update=os.environ.get("DEFERRED", "1") == "1")
+ts = TrainStep(model, configs.LOSS_WEIGHTS, bf16=True, capturable=True, deferred_update=os.environ.get("DEFERRED", "0") == "1")
 hb = bench.pinned_batch(32, 800, 150, seed=1000)
 b = bench.to_device(hb, dev)
 ts.capture(b)
