@@ -19,6 +19,7 @@ _forced_precision = None
 
 
 _direct_grad = False
+_grads_zeroed = False       # set by a trainer that KNOWS every .grad it sinks into is zero when backward starts (see below)
 flow_grads_ready = None     # optional callable(flow_index, final): invoked by the flow stack's backward right after the
                             # last kernel producing flow `flow_index`'s parameter-network gradients has been enqueued;
                             # final=True when every one of them went straight into .grad (direct accumulation)
@@ -38,18 +39,22 @@ class trainer_scope:
     `flow_grads_ready` callback are process-global switches, so they are set on entry and restored on exit -- another
     TrainStep, or any other user of the flow stack in the same process, never inherits them."""
 
-    def __init__(self, direct_grad, on_flow_grads=None):
-        self.new = (bool(direct_grad), on_flow_grads)
+    def __init__(self, direct_grad, on_flow_grads=None, grads_zeroed=False):
+        """grads_zeroed: the trainer guarantees that the .grad buffers are zero when backward starts and that there is ONE
+        backward per optimizer step (TrainStep with the fused optimizer: the update zeroes them in the pass that consumes
+        them).  The weight-norm backward then STORES weight_v / weight_g gradients instead of read-modify-writing 118 MB of
+        zeros per flow."""
+        self.new = (bool(direct_grad), on_flow_grads, bool(grads_zeroed) and bool(direct_grad))
 
     def __enter__(self):
-        global _direct_grad, flow_grads_ready
-        self.prev = (_direct_grad, flow_grads_ready)
-        _direct_grad, flow_grads_ready = self.new
+        global _direct_grad, flow_grads_ready, _grads_zeroed
+        self.prev = (_direct_grad, flow_grads_ready, _grads_zeroed)
+        _direct_grad, flow_grads_ready, _grads_zeroed = self.new
         return self
 
     def __exit__(self, *exc):
-        global _direct_grad, flow_grads_ready
-        _direct_grad, flow_grads_ready = self.prev
+        global _direct_grad, flow_grads_ready, _grads_zeroed
+        _direct_grad, flow_grads_ready, _grads_zeroed = self.prev
         return False
 
 

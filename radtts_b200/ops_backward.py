@@ -131,7 +131,8 @@ def flow_stack_backward(saved, g_zout, g_log_s):
             wg.gv_in[j], wg.gg_in[j] = ops._p(outs[idx_v[1 + j]]), ops._p(outs[idx_g[1 + j]])
             wg.gv_rs[j], wg.gg_rs[j] = ops._p(outs[idx_v[1 + nl + j]]), ops._p(outs[idx_g[1 + nl + j]])
         _lib.check(L.radtts_flow_weight_norm_backward(ctypes.byref(dims), ctypes.byref(wstruct), ctypes.byref(g),
-                                                      ctypes.byref(wg), 1 if direct else 0, tail_stream),
+                                                      ctypes.byref(wg), 1 if (direct and not ops._grads_zeroed) else 0,
+                                                      tail_stream),
                    "radtts_flow_weight_norm_backward")
         out = [None] * n_per
         out[0] = gw_inv_full[dims.c_off:, dims.c_off:]

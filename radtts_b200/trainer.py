@@ -203,7 +203,10 @@ class TrainStep:
             self._grads_clean = False
         else:
             self.optimizer.zero_grad(set_to_none=True)
-        with ops.trainer_scope(self.fused_optimizer, self._on_flow_grads if self.ev_flow else None):
+        # (fused optimizer: the flat gradient buffer is zero here -- memset above or zeroed by the previous update -- and
+        # this is the step's only backward, so weight-norm gradients are stored, not accumulated)
+        with ops.trainer_scope(self.fused_optimizer, self._on_flow_grads if self.ev_flow else None,
+                               grads_zeroed=self.fused_optimizer):
             total, _ = self.forward_loss(batch)
             total.backward()
         return total.detach()
